@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""Headline benchmark: input Msps through the int8 -> mix -> FIR -> demod -> audio-FIR chain.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the fp64 oracle port on host cores
+
+Workload = BASELINE.json configs[1] (C2, AM broadcast chain): per GPU and per step one block of 2^28
+synthetic int8 IQ samples (512 MiB, larger than L2, so no L2 flush is needed between iterations)
+-> mix by -1.234 MHz -> 101-tap low-pass, decimate by 40 -> |.| -> 129-tap low-pass, decimate by 10
+-> 48 kHz-class audio.  At N > 1 every rank processes its own time segment of one long stream
+(no collective on the filter path) and the decimated audio is gathered to rank 0 over NCCL inside the
+timed region; per-GPU work is fixed, so scaling is "weak".
+
+One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 19.2e6            # 48 kHz x 40 x 10 ("20 Msps-class")
+F_SHIFT = -1.234e6
+T1, D1, T2, D2 = 101, 40, 129, 10
+LOG2_BLOCK = 28
+METRIC = "input Msps through int8->mix->FIR->demod chain"
+UNIT = "Msps"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--log2-block", type=int, default=LOG2_BLOCK, help="log2 of input samples per GPU per step")
+    ap.add_argument("--workload", choices=["am", "wbfm"], default="am")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def workload(name: str):
+    from cuda_sdr_b200 import taps
+    if name == "am":
+        return dict(name="C2 AM broadcast chain", fs=FS, f=F_SHIFT, t1=taps.lowpass(T1, 0.45 * FS / D1, FS), d1=D1, mod=0, gain=1.0,
+                    t2=taps.lowpass(T2, 0.45 * 48e3, FS / D1), d2=D2)
+    from cuda_sdr_b200 import fm_gain
+    return dict(name="C3 WBFM chain", fs=FS, f=2.5e6, t1=taps.lowpass(545, 100e3, FS), d1=80, mod=1, gain=fm_gain(FS / 80, 75e3),
+                t2=taps.lowpass(273, 0.45 * 48e3, FS / 80), d2=5)
+
+
+def config_dict(args, wl, extra=None):
+    n = 1 << args.log2_block
+    cfg = {
+        "workload": f"{wl['name']}: 2^{args.log2_block} synthetic int8 IQ samples per GPU per step at {wl['fs'] / 1e6:.1f} Msps-class rate "
+                    f"-> mix -> {len(wl['t1'])}-tap FIR decimate-by-{wl['d1']} -> {'AM' if wl['mod'] == 0 else 'FM'} demod -> "
+                    f"{len(wl['t2'])}-tap audio FIR decimate-by-{wl['d2']}",
+        "samples_per_gpu_per_step": n,
+        "rf_taps": len(wl["t1"]), "rf_decimation": wl["d1"], "audio_taps": len(wl["t2"]), "audio_decimation": wl["d2"],
+        "modulation": "am" if wl["mod"] == 0 else "fm",
+        "phase_mode": "exact (64-bit fixed-point turns)",
+        "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
+        "parallelism": "overlapped time segments, one per GPU; NCCL send/recv gather of audio to rank 0",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the power range seen
+        lo, hi = min(power), max(power)
+        loaded = [c for c, p in zip(sm, power) if p >= lo + 0.5 * (hi - lo)] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": hi}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (fp64, OpenMP) on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------
+def cpu_chain_rate(wl, target_seconds: float, max_log2: int = 26):
+    """Returns (Msps, cores, sample description, samples, seconds) for the fp64 oracle on host cores."""
+    import numpy as np
+    from oracle import oracle as orc
+
+    spec = orc.ChainSpec(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], wl["gain"], wl["t2"], wl["d2"])
+    rng = np.random.default_rng(0x5D120001)
+    probe = 1 << 20
+    x = rng.integers(-100, 101, size=2 * probe, dtype=np.int8)
+    orc.chain(spec, x)  # warm up threads and pages
+    t0 = time.perf_counter()
+    orc.chain(spec, x)
+    rate = probe / (time.perf_counter() - t0)
+    log2 = max(20, min(max_log2, int(np.floor(np.log2(max(rate * target_seconds, 1.0))))))
+    n = 1 << log2
+    x = rng.integers(-100, 101, size=2 * n, dtype=np.int8)
+    t0 = time.perf_counter()
+    out, _, _ = orc.chain(spec, x)
+    dt = time.perf_counter() - t0
+    assert out.size == spec.num_outputs(n)
+    return n / dt / 1e6, orc.num_threads(), f"2^{log2} samples of the same workload, one pass, fp64 oracle (oracle/oracle.c), OpenMP", n, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = workload(args.workload)
+    import numpy as np
+    from oracle import oracle as orc
+
+    spec = orc.ChainSpec(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], wl["gain"], wl["t2"], wl["d2"])
+    # bounded sample per step so that steps+warmup finish within minutes on any host
+    rng = np.random.default_rng(0x5D120001)
+    probe = 1 << 20
+    x = rng.integers(-100, 101, size=2 * probe, dtype=np.int8)
+    orc.chain(spec, x)
+    t0 = time.perf_counter()
+    orc.chain(spec, x)
+    rate = probe / (time.perf_counter() - t0)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    log2 = max(20, min(26, int(np.floor(np.log2(max(rate * min(budget, 10.0), 1.0))))))
+    n = 1 << log2
+    x = rng.integers(-100, 101, size=2 * n, dtype=np.int8)
+    for _ in range(args.warmup):
+        orc.chain(spec, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.chain(spec, x)
+    dt = time.perf_counter() - t0
+    msps = n * args.steps / dt / 1e6
+    sample = f"each step = 2^{log2} samples of the workload (bounded sample), fp64 oracle port on host cores, OpenMP"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": msps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, wl, {"note": "the reference has no CPU DSP path and its kernels (gsdr) are absent; this arm is the "
+                                                  "repo's CPU restatement (oracle port), not the reference's CUDA pipeline"}),
+        "cpu_baseline": {"value": msps, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import cuda_sdr_b200 as sdr
+    from cuda_sdr_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = workload(args.workload)
+    n = 1 << args.log2_block
+    chain = sdr.Chain(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], fm_gain=wl["gain"], audio_taps=wl["t2"], audio_decim=wl["d2"],
+                      device=local_rank)
+    n_rf, n_demod, n_audio = chain.counts(n)
+    x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120001 + rank)  # this rank's time segment of the stream
+    demod = torch.empty(n_demod, dtype=torch.float32, device=dev)
+    audio = torch.empty(n_audio, dtype=torch.float32, device=dev)
+    first_index = rank * n  # absolute sample index of the segment (mixer phase)
+    counts = [n_audio] * world
+    gathered = torch.empty(n_audio * world, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+
+    def gather():
+        if world == 1:
+            return
+        if rank == 0:
+            gathered[:n_audio] = audio
+            reqs = [dist.irecv(gathered[r * n_audio:(r + 1) * n_audio], src=r) for r in range(1, world)]
+            for r in reqs:
+                r.wait()
+        else:
+            dist.send(audio, dst=0)
+
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k2_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i=None):
+        if i is not None:
+            k1_events[i][0].record()
+        chain.rf_stage(x, n_demod, first_index, out=demod, n_in=n)
+        if i is not None:
+            k1_events[i][1].record()
+            k2_events[i][0].record()
+        chain.audio_stage(demod, n_audio, out=audio)
+        if i is not None:
+            k2_events[i][1].record()
+        gather()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = sdr._native.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        step(i)
+    t_end.record()
+    barrier()
+    launches = sdr._native.launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    k1_ms = statistics.mean(a.elapsed_time(b) for a, b in k1_events)
+    k2_ms = statistics.mean(a.elapsed_time(b) for a, b in k2_events)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+
+    # ---- end to end: host (pinned) input -> C-ABI host call -> host output, H2D/D2H inside the timed region
+    e2e = None
+    if not args.skip_e2e:
+        xh = torch.empty(2 * n, dtype=torch.int8).pin_memory()
+        xh.copy_(x)
+        outh = torch.empty(n_audio, dtype=torch.float32).pin_memory()
+        e2e_steps = max(2, min(args.steps, 5))
+        chain.process_host(xh, first_index, out=outh)  # warm-up: allocates the staging slots
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            got = chain.process_host(xh, first_index, out=outh)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert got.numel() == n_audio
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * n * e2e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n_audio,
+               "steps": e2e_steps, "api": "b200sdr_chain_process_host (pinned host buffers; double-buffered H2D/K1/K2/D2H)"}
+        del xh
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = n * (2.0 + 4.0 / wl["d1"])  # K1: 2 B/sample int8 IQ in, one float per D1 samples out
+        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, wl, {"k1_variant": chain.variant}),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "K1 rowsKernel (convert+mix+FIR+decimate+demod)", "kernel_ms": k1_ms, "k2_ms": k2_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.skip_cpu:
+            v, cores, sample, _, _ = cpu_chain_rate(wl, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

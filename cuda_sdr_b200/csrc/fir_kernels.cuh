@@ -1,0 +1,446 @@
+// Decimating-FIR kernels of the hot path (sm_100a).
+//
+//   rowsKernel   -- the fast path.  One thread owns RPT "rows" of D consecutive input samples (one
+//                   decimation period each).  With taps re-laid out as hT[p][m] = h[m*D + p] a row q
+//                   contributes the M = ceil(T/D) partial sums
+//                       P[q][m] = sum_{p<D} hT[p][m] * z[q*D + p],      y[k] = sum_{m<M} P[k+m][m]
+//                   so every input sample is converted and mixed exactly ONCE and only kept outputs are
+//                   computed (polyphase decimation).  The raw tile (rows x D samples, int8 or float) is
+//                   staged in shared memory by one 1-D TMA bulk copy; taps, the per-phase mixer table
+//                   W[p] = exp(j*w*p) and the per-partial rotations exp(j*w*m*D) sit in shared memory and
+//                   are read as warp-wide broadcasts; the partial sums are exchanged through shared
+//                   memory once per tile.  The per-row carrier phase exp(j*w*q*D) never has to be
+//                   evaluated for AM/FM outputs (|.| and the discriminator are invariant to it).
+//   directKernel -- generic fallback for any (T, D), alignment and tap type: one thread per output,
+//                   taps (optionally pre-multiplied by the mixer phasor) chunked through shared memory.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200sdr {
+
+enum ElemKind : int { kElemInt8Complex = 0, kElemComplex = 1, kElemReal = 2 };
+enum ModKind : int { kModAm = 0, kModFm = 1, kModNone = 2 };
+
+struct FirParams {
+  const void* in;          // input elements (int8 pairs / float2 / float)
+  void* out;               // float (AM/FM or real data) or float2
+  const float* taps;       // raw device taps: T floats (real) or T float2 (complex); may be null if tables given
+  const float* tapTable;   // rows path: hT[D][MP], pre-scaled; null -> built from `taps` in the prologue
+  const float2* mixTable;  // rows path: W[D] (already scaled by inScale); null -> computed from phaseStep
+  const float2* rotTable;  // rows path: exp(j*w*m*D), m <= MP; null -> computed from phaseStep
+  unsigned long long nOut;
+  unsigned long long nIn;  // valid input elements starting at `in`
+  unsigned long long firstIndex;  // absolute sample index of in[0] (mixer phase)
+  unsigned long long phaseStep;   // 2^64 * frac(f/fs)
+  unsigned T, D, M;
+  unsigned rowsPerTile, outPerTile;
+  int mod;        // ModKind of the epilogue
+  float gain;     // FM
+  float inScale;  // 1/128 for int8 input, 1 otherwise
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float2 phasorOfTurns(unsigned long long turns) {
+  // turns is a 0.64 fixed-point fraction of a revolution; the signed view keeps |x| <= 1 for sincospif
+  const float x = static_cast<float>(static_cast<long long>(turns)) * (2.0f / 18446744073709551616.0f);
+  float s, c;
+  sincospif(x, &s, &c);
+  return make_float2(c, s);
+}
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+  return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.y, b.x, a.x * b.y));
+}
+
+__device__ __forceinline__ void storeDemod(int mod, void* out, unsigned long long k, float2 cur, float2 next, float2 rot1, float2 carrier, float gain) {
+  if (mod == kModAm) {
+    static_cast<float*>(out)[k] = sqrtf(fmaf(cur.x, cur.x, cur.y * cur.y));
+  } else if (mod == kModFm) {
+    const float2 d = make_float2(fmaf(next.y, cur.y, next.x * cur.x), fmaf(next.y, cur.x, -next.x * cur.y));
+    const float2 r = cmulf(d, rot1);
+    static_cast<float*>(out)[k] = gain * atan2f(r.y, r.x);
+  } else {
+    static_cast<float2*>(out)[k] = cmulf(cur, carrier);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rows kernel
+// ------------------------------------------------------------------------------------------------
+template <int ELEM>
+struct ElemTraits;
+template <>
+struct ElemTraits<kElemInt8Complex> {
+  static constexpr int kBytes = 2, kVec = 8;
+};
+template <>
+struct ElemTraits<kElemComplex> {
+  static constexpr int kBytes = 8, kVec = 2;
+};
+
+constexpr int kRowsThreads = 128;
+
+template <int MP>
+__device__ __forceinline__ void loadTapRow(const float* hT, unsigned p, float (&h)[MP]) {
+  if constexpr (MP == 1) {
+    h[0] = hT[p];
+  } else if constexpr (MP == 2) {
+    const float2 v = reinterpret_cast<const float2*>(hT)[p];
+    h[0] = v.x;
+    h[1] = v.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < MP / 4; i++) {
+      const float4 v = reinterpret_cast<const float4*>(hT)[p * (MP / 4) + i];
+      h[4 * i] = v.x;
+      h[4 * i + 1] = v.y;
+      h[4 * i + 2] = v.z;
+      h[4 * i + 3] = v.w;
+    }
+  }
+}
+
+// Shared-memory carve-up (bytes), identical on host and device.
+struct RowsSmem {
+  unsigned mixOff, rotOff, tapOff, tileOff, total;
+};
+__host__ __device__ inline RowsSmem rowsSmemLayout(unsigned D, unsigned MP, unsigned M, unsigned rowsPerTile, unsigned elemBytes, bool fm) {
+  RowsSmem s;
+  unsigned off = 16;  // mbarrier
+  s.mixOff = off;
+  off += D * 8;
+  s.rotOff = off;
+  off += (MP + 1) * 8;
+  off = (off + 15u) & ~15u;
+  s.tapOff = off;
+  off += D * MP * 4;
+  off = (off + 127u) & ~127u;
+  s.tileOff = off;
+  const unsigned tileBytes = rowsPerTile * D * elemBytes;
+  const unsigned exchBytes = (M > 0 ? (M - 1) : 0) * rowsPerTile * 8 + (fm ? rowsPerTile * 8 : 0);
+  off += tileBytes > exchBytes ? tileBytes : exchBytes;
+  s.total = off;
+  return s;
+}
+
+template <int ELEM, bool MIX, int MP, int RPT>
+__global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) {
+  using Traits = ElemTraits<ELEM>;
+  constexpr int ES = Traits::kBytes;
+  constexpr int VEC = Traits::kVec;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const unsigned D = prm.D, M = prm.M, NT = prm.rowsPerTile;
+  const RowsSmem lay = rowsSmemLayout(D, MP, M, NT, ES, prm.mod == kModFm);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float2* W = reinterpret_cast<float2*>(smem + lay.mixOff);
+  float2* rot = reinterpret_cast<float2*>(smem + lay.rotOff);
+  float* hT = reinterpret_cast<float*>(smem + lay.tapOff);
+  unsigned char* tile = smem + lay.tileOff;
+
+  const unsigned tid = threadIdx.x;
+  const unsigned long long row0 = static_cast<unsigned long long>(blockIdx.x) * prm.outPerTile;
+
+  // ---- stage the raw tile with one TMA bulk copy ---------------------------------------------------
+  const unsigned long long tileStart = row0 * D * ES;
+  const unsigned long long totalBytes = prm.nIn * ES;
+  const unsigned tileBytes = NT * D * ES;
+  const unsigned avail = totalBytes - tileStart < tileBytes ? static_cast<unsigned>(totalBytes - tileStart) : tileBytes;
+  const unsigned bulk = avail & ~15u;
+  if (tid == 0) {
+    mbarInit(bar, 1);
+    fenceMbarInit();
+    mbarExpectTx(bar, bulk);
+    if (bulk) tmaBulkLoad(tile, static_cast<const unsigned char*>(prm.in) + tileStart, bulk, bar);
+  }
+  // tail of the last tile: copy the <16 B remainder and zero what lies past the valid input
+  for (unsigned b = bulk + tid; b < tileBytes; b += kRowsThreads) {
+    tile[b] = b < avail ? static_cast<const unsigned char*>(prm.in)[tileStart + b] : 0;
+  }
+
+  // ---- tables ----------------------------------------------------------------------------------------
+  for (unsigned i = tid; i < D * MP; i += kRowsThreads) {
+    float v;
+    if (prm.tapTable) {
+      v = prm.tapTable[i];
+    } else {
+      const unsigned p = i / MP, m = i % MP;
+      const unsigned j = m * D + p;
+      v = (m < M && j < prm.T) ? prm.taps[j] * (MIX ? 1.0f : prm.inScale) : 0.0f;
+    }
+    hT[i] = v;
+  }
+  if constexpr (MIX) {
+    for (unsigned p = tid; p < D; p += kRowsThreads) {
+      float2 w;
+      if (prm.mixTable) {
+        w = prm.mixTable[p];
+      } else {
+        w = phasorOfTurns(prm.phaseStep * p);
+        w.x *= prm.inScale;
+        w.y *= prm.inScale;
+      }
+      W[p] = w;
+    }
+    if (tid <= MP) {
+      rot[tid] = prm.rotTable ? prm.rotTable[tid] : phasorOfTurns(prm.phaseStep * (static_cast<unsigned long long>(tid) * D));
+    }
+  }
+  __syncthreads();
+  mbarWait(bar, 0);
+
+  // ---- main loop: convert + mix once per sample, M partial sums per row ----------------------------------
+  float2 acc[RPT][MP];
+#pragma unroll
+  for (int i = 0; i < RPT; i++)
+#pragma unroll
+    for (int m = 0; m < MP; m++) acc[i][m] = make_float2(0.0f, 0.0f);
+
+  const unsigned rowBytes = D * ES;
+  const unsigned char* rowPtr[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; i++) rowPtr[i] = tile + (tid + i * kRowsThreads) * rowBytes;
+
+  for (unsigned p = 0; p < D; p += VEC) {
+    uint4 v[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; i++) v[i] = *reinterpret_cast<const uint4*>(rowPtr[i] + p * ES);
+
+    if constexpr (ELEM == kElemInt8Complex) {
+#pragma unroll
+      for (int s = 0; s < 4; s++) {  // word s holds samples p+2s and p+2s+1 as I,Q,I,Q bytes
+        float h0[MP], h1[MP];
+        loadTapRow<MP>(hT, p + 2 * s, h0);
+        loadTapRow<MP>(hT, p + 2 * s + 1, h1);
+        float2 w0, w1;
+        if constexpr (MIX) {
+          w0 = W[p + 2 * s];
+          w1 = W[p + 2 * s + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; i++) {
+          const uint32_t word = s == 0 ? v[i].x : s == 1 ? v[i].y : s == 2 ? v[i].z : v[i].w;
+          float a, b, c, d;
+          int8x4ToFloat(word, a, b, c, d);
+          float2 z0 = make_float2(a, b), z1 = make_float2(c, d);
+          if constexpr (MIX) {
+            z0 = cmulf(z0, w0);
+            z1 = cmulf(z1, w1);
+          }
+#pragma unroll
+          for (int m = 0; m < MP; m++) {
+            acc[i][m].x = fmaf(h0[m], z0.x, acc[i][m].x);
+            acc[i][m].y = fmaf(h0[m], z0.y, acc[i][m].y);
+            acc[i][m].x = fmaf(h1[m], z1.x, acc[i][m].x);
+            acc[i][m].y = fmaf(h1[m], z1.y, acc[i][m].y);
+          }
+        }
+      }
+    } else {
+      float h0[MP], h1[MP];
+      loadTapRow<MP>(hT, p, h0);
+      loadTapRow<MP>(hT, p + 1, h1);
+      float2 w0, w1;
+      if constexpr (MIX) {
+        w0 = W[p];
+        w1 = W[p + 1];
+      }
+#pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        float2 z0 = make_float2(__uint_as_float(v[i].x), __uint_as_float(v[i].y));
+        float2 z1 = make_float2(__uint_as_float(v[i].z), __uint_as_float(v[i].w));
+        if constexpr (MIX) {
+          z0 = cmulf(z0, w0);
+          z1 = cmulf(z1, w1);
+        }
+#pragma unroll
+        for (int m = 0; m < MP; m++) {
+          acc[i][m].x = fmaf(h0[m], z0.x, acc[i][m].x);
+          acc[i][m].y = fmaf(h0[m], z0.y, acc[i][m].y);
+          acc[i][m].x = fmaf(h1[m], z1.x, acc[i][m].x);
+          acc[i][m].y = fmaf(h1[m], z1.y, acc[i][m].y);
+        }
+      }
+    }
+  }
+
+  // ---- exchange partial sums: y[k] = P[k][0] + sum_{m>=1} rot[m] * P[k+m][m] -------------------------
+  float2* part = reinterpret_cast<float2*>(tile);       // [(m-1)*NT + row]
+  float2* sums = part + (M > 0 ? (M - 1) : 0) * NT;     // FM only: S[row]
+  if (MP > 1 && M > 1) {
+    __syncthreads();  // everyone is done reading the tile; it is reused for the exchange
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+      const unsigned row = tid + i * kRowsThreads;
+#pragma unroll
+      for (int m = 1; m < MP; m++) {
+        if (m < M) {
+          float2 v = acc[i][m];
+          if constexpr (MIX) v = cmulf(v, rot[m]);
+          part[(m - 1) * NT + row] = v;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+      const unsigned row = tid + i * kRowsThreads;
+#pragma unroll
+      for (int m = 1; m < MP; m++) {
+        if (m < M && row + m < NT) {
+          const float2 v = part[(m - 1) * NT + row + m];
+          acc[i][0].x += v.x;
+          acc[i][0].y += v.y;
+        }
+      }
+    }
+  }
+
+  float2 rot1 = make_float2(1.0f, 0.0f);
+  if constexpr (MIX) rot1 = rot[1];
+
+  if (prm.mod == kModFm) {
+    if (!(MP > 1 && M > 1)) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RPT; i++) sums[tid + i * kRowsThreads] = acc[i][0];
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < RPT; i++) {
+    const unsigned row = tid + i * kRowsThreads;
+    const unsigned long long k = row0 + row;
+    if (row < prm.outPerTile && k < prm.nOut) {
+      float2 next = make_float2(0.0f, 0.0f), carrier = make_float2(1.0f, 0.0f);
+      if (prm.mod == kModFm) next = sums[row + 1];
+      if (MIX && prm.mod == kModNone) carrier = phasorOfTurns(prm.phaseStep * (prm.firstIndex + k * D));
+      storeDemod(prm.mod, prm.out, k, acc[i][0], next, rot1, carrier, prm.gain);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct kernel (fallback): thread per output, taps chunked through shared memory as float2 (real
+// taps carry a zero imaginary part unless the mixer phasor is folded in).  When the block's input
+// window ((outPerBlock-1)*D + T elements) fits in shared memory it is staged there with coalesced loads
+// (STAGED), which is what the audio-rate FIR of the chain uses; otherwise inputs come through L1.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDirectThreads = 256;
+constexpr int kDirectTapChunk = 1024;
+constexpr unsigned kDirectFixedSmem = kDirectTapChunk * 8 + kDirectThreads * 8;
+
+template <int ELEM>
+struct RawElem;
+template <>
+struct RawElem<kElemInt8Complex> {
+  using type = char2;
+};
+template <>
+struct RawElem<kElemComplex> {
+  using type = float2;
+};
+template <>
+struct RawElem<kElemReal> {
+  using type = float;
+};
+
+template <int ELEM>
+__device__ __forceinline__ float2 elemToComplex(typename RawElem<ELEM>::type v, float scale) {
+  if constexpr (ELEM == kElemInt8Complex) {
+    return make_float2(static_cast<float>(v.x) * scale, static_cast<float>(v.y) * scale);
+  } else if constexpr (ELEM == kElemComplex) {
+    return v;
+  } else {
+    return make_float2(v, 0.0f);
+  }
+}
+
+// TAPC: taps are complex (FirCC/FirCF).  REALOUT: real data with real taps -> float output.
+template <int ELEM, bool TAPC, bool MIX, bool REALOUT, bool STAGED>
+__global__ void __launch_bounds__(kDirectThreads) directKernel(const FirParams prm) {
+  using Raw = typename RawElem<ELEM>::type;
+  extern __shared__ __align__(16) unsigned char dsmem[];
+  float2* sTaps = reinterpret_cast<float2*>(dsmem);
+  float2* sY = sTaps + kDirectTapChunk;
+  Raw* sIn = reinterpret_cast<Raw*>(dsmem + kDirectFixedSmem);
+
+  const unsigned tid = threadIdx.x;
+  const unsigned outPerBlock = prm.mod == kModFm ? kDirectThreads - 1 : kDirectThreads;
+  const unsigned long long k0 = static_cast<unsigned long long>(blockIdx.x) * outPerBlock;
+  const unsigned long long k = k0 + tid;
+  // FM needs FIR output k+1 as well: the block computes one more FIR output than it stores.
+  const unsigned long long nFir = prm.mod == kModFm ? prm.nOut + 1 : prm.nOut;
+  const bool active = k < nFir;
+  const unsigned long long base = k * prm.D;
+  const Raw* gIn = static_cast<const Raw*>(prm.in);
+
+  if constexpr (STAGED) {
+    const unsigned long long first = k0 * prm.D;
+    const unsigned tileElems = (kDirectThreads - 1) * prm.D + prm.T;
+    for (unsigned i = tid; i < tileElems; i += kDirectThreads) {
+      Raw v {};
+      if (first + i < prm.nIn) v = gIn[first + i];
+      sIn[i] = v;
+    }
+  }
+
+  float2 acc = make_float2(0.0f, 0.0f);
+  for (unsigned c0 = 0; c0 < prm.T; c0 += kDirectTapChunk) {
+    const unsigned cn = prm.T - c0 < kDirectTapChunk ? prm.T - c0 : kDirectTapChunk;
+    __syncthreads();
+    for (unsigned j = tid; j < cn; j += kDirectThreads) {
+      float2 h;
+      if constexpr (TAPC) {
+        h = reinterpret_cast<const float2*>(prm.taps)[c0 + j];
+      } else {
+        h = make_float2(prm.taps[c0 + j], 0.0f);
+      }
+      if constexpr (MIX) h = cmulf(h, phasorOfTurns(prm.phaseStep * (c0 + j)));
+      sTaps[j] = h;
+    }
+    __syncthreads();
+    if (active) {
+      const Raw* src = STAGED ? sIn + (tid * prm.D + c0) : gIn + (base + c0);
+#pragma unroll 4
+      for (unsigned j = 0; j < cn; j++) {
+        const float2 x = elemToComplex<ELEM>(src[j], prm.inScale);
+        const float2 h = sTaps[j];
+        if constexpr (ELEM == kElemReal) {
+          acc.x = fmaf(h.x, x.x, acc.x);
+          if constexpr (TAPC) acc.y = fmaf(h.y, x.x, acc.y);
+        } else if constexpr (TAPC || MIX) {
+          acc.x = fmaf(h.x, x.x, acc.x);
+          acc.x = fmaf(-h.y, x.y, acc.x);
+          acc.y = fmaf(h.x, x.y, acc.y);
+          acc.y = fmaf(h.y, x.x, acc.y);
+        } else {
+          acc.x = fmaf(h.x, x.x, acc.x);
+          acc.y = fmaf(h.x, x.y, acc.y);
+        }
+      }
+    }
+  }
+
+  if constexpr (REALOUT) {
+    if (active) static_cast<float*>(prm.out)[k] = acc.x;
+    return;
+  }
+
+  float2 rot1 = make_float2(1.0f, 0.0f), carrier = make_float2(1.0f, 0.0f), next = make_float2(0.0f, 0.0f);
+  if constexpr (MIX) rot1 = phasorOfTurns(prm.phaseStep * static_cast<unsigned long long>(prm.D));
+  if (prm.mod == kModFm) {
+    sY[tid] = acc;
+    __syncthreads();
+    if (tid + 1 < kDirectThreads) next = sY[tid + 1];
+  }
+  if (tid < outPerBlock && k < prm.nOut) {
+    if (MIX && prm.mod == kModNone) carrier = phasorOfTurns(prm.phaseStep * (prm.firstIndex + base));
+    storeDemod(prm.mod, prm.out, k, acc, next, rot1, carrier, prm.gain);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200sdr

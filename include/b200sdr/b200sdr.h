@@ -1,0 +1,125 @@
+/*
+ * b200sdr.h -- C-ABI of the fused int8/cf32 -> mix -> decimating FIR -> AM/FM demod -> audio FIR chain.
+ *
+ * Plain pointers and sizes only.  This is the boundary the host framework (libgpusdrpipeline:
+ * getFactoriesSingleton()/IFactories, include/gpusdrpipeline/) and any foreign-language binding sit on.
+ * One `b200sdr_chain` replaces, as ONE node, the five-node graph the reference builds in
+ *   src/filters/factories/RfToPcmAudioFactory.cpp:214-304  (cosine -> multiply -> Fir -> QuadDemod -> Fir)
+ * preceded by src/filters/Int8ToFloat.cpp, i.e. the reference call sequence
+ *   src/applications/nbfm_test.cpp:256-354.
+ *
+ * Status codes are the reference's `Status` values (include/gpusdrpipeline/Status.h:22-34).
+ * No CPU fallback exists: every compute entry point needs a CUDA device and fails loudly without one.
+ */
+#ifndef B200SDR_B200SDR_H
+#define B200SDR_B200SDR_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define B200SDR_C_LINKAGE extern "C"
+#else
+#define B200SDR_C_LINKAGE
+#endif
+#define B200SDR_EXPORT B200SDR_C_LINKAGE __attribute__((visibility("default")))
+
+typedef uint32_t b200sdr_status; /* Status.h:22-34 */
+enum {
+  B200SDR_OK = 0,
+  B200SDR_UNKNOWN_ERROR = 1,
+  B200SDR_OUT_OF_MEMORY = 2,
+  B200SDR_RUNTIME_ERROR = 3,
+  B200SDR_INVALID_ARGUMENT = 4,
+  B200SDR_INVALID_STATE = 5,
+  B200SDR_OUT_OF_RANGE = 6,
+};
+
+/* input_type uses the reference's SampleType values (include/gpusdrpipeline/SampleType.h:20-25) */
+enum { B200SDR_INPUT_CF32 = 0, B200SDR_INPUT_INT8 = 2 };
+/* modulation uses the reference's Modulation values (Modulation.h:22-26) plus "none" */
+enum { B200SDR_MOD_AM = 0, B200SDR_MOD_FM = 1, B200SDR_MOD_NONE = 2 };
+
+typedef struct b200sdr_chain_config {
+  uint32_t struct_size;  /* sizeof(b200sdr_chain_config), for forward compatibility */
+  uint32_t input_type;   /* B200SDR_INPUT_*: interleaved int8 IQ (HackRF format) or cuComplex */
+  uint32_t modulation;   /* B200SDR_MOD_* */
+  uint32_t mix;          /* 0: no mixer; 1: multiply by exp(+j*2*pi*frequency/sample_rate*n) */
+  double sample_rate;    /* Hz, of the input */
+  double frequency;      /* Hz; the cosine-source frequency (tuned - channel), RfToPcmAudioFactory.cpp:225 */
+  const float* rf_taps;  /* HOST pointer, correlation order (as passed to IFirFactory::createFir) */
+  size_t rf_tap_count;
+  size_t rf_decimation;
+  float fm_gain;         /* QuadDemodFactory.h:108-110; ignored unless FM */
+  uint32_t reserved0;
+  const float* audio_taps; /* HOST pointer or NULL: no audio FIR (output = demodulated samples) */
+  size_t audio_tap_count;
+  size_t audio_decimation;
+  int32_t cuda_device;
+  uint32_t reserved1;
+} b200sdr_chain_config;
+
+typedef struct b200sdr_chain b200sdr_chain;
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* config, b200sdr_chain** chainOut);
+B200SDR_EXPORT void b200sdr_chain_destroy(b200sdr_chain* chain);
+B200SDR_EXPORT const char* b200sdr_last_error(void); /* thread-local, never NULL */
+
+/* ---- sample-count rules (pure host arithmetic; usable without a GPU) --------------------------- */
+/* Fir::getNumOutputElements (Fir.cpp:141-187) in its well-defined form: nIn+1 >= T ? (nIn+1-T)/D : 0 */
+B200SDR_EXPORT size_t b200sdr_fir_num_outputs(size_t numInputs, size_t tapCount, size_t decimation);
+/* Outputs of each stage for numInputs input samples: RF FIR, demodulator (FM keeps one sample of
+ * history, QuadFmDemod.cpp:76-84), audio FIR.  Any out pointer may be NULL. */
+B200SDR_EXPORT void b200sdr_chain_counts(
+    const b200sdr_chain* chain, size_t numInputs, size_t* numRf, size_t* numDemod, size_t* numAudio);
+/* Input samples that one block producing numAudio final outputs reads, and the input stride between
+ * consecutive final outputs (D1*D2).  span(numAudio) = (numAudio-1)*stride + window. */
+B200SDR_EXPORT size_t b200sdr_chain_input_stride(const b200sdr_chain* chain);
+B200SDR_EXPORT size_t b200sdr_chain_input_window(const b200sdr_chain* chain);
+/* 64-bit fixed-point mixer phase increment: round(frac(frequency/sampleRate) * 2^64). */
+B200SDR_EXPORT uint64_t b200sdr_phase_step(double frequency, double sampleRate);
+
+/* Split `numAudio` final outputs into `parts` contiguous segments (time-segment sharding over GPUs or
+ * over staged host chunks).  For part `index` returns the first output, the output count, the first
+ * input sample it reads and the number of input samples it reads (overlap = look-ahead halo). */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_segment(
+    const b200sdr_chain* chain, size_t numAudio, size_t parts, size_t index, size_t* firstOutput, size_t* outputCount,
+    size_t* firstInput, size_t* inputCount);
+
+/* ---- device-resident processing (pointers are DEVICE pointers; async on `stream`) ---------------- */
+/* Stage K1: convert + mix + decimating FIR + demod in one kernel.  `numOutputs` demodulated floats
+ * (AM/FM) or complex RF-FIR samples (NONE) are written to `output`.  `firstSampleIndex` is the absolute
+ * index of input[0] (mixer phase; irrelevant to AM/FM results).  `numInputs` bounds the reads. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_rf_stage(
+    b200sdr_chain* chain, const void* input, size_t numInputs, uint64_t firstSampleIndex, void* output,
+    size_t numOutputs, cudaStream_t stream);
+/* Stage K2: audio FIR (float taps, float data, decimating). */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_audio_stage(
+    b200sdr_chain* chain, const float* demod, float* audio, size_t numAudio, cudaStream_t stream);
+/* K1 + K2 over one block.  `demodScratch` must hold numDemod floats (see b200sdr_chain_counts).
+ * *numAudioOut receives the number of final outputs written to `audio`. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_process_device(
+    b200sdr_chain* chain, const void* input, size_t numInputs, uint64_t firstSampleIndex, float* demodScratch,
+    float* audio, size_t audioCapacity, size_t* numAudioOut, cudaStream_t stream);
+
+/* ---- host-buffer processing (the end-to-end path) ------------------------------------------------ */
+/* Processes a block that lives in HOST memory (pinned for full PCIe rate) and returns the final
+ * outputs in HOST memory.  Internally: the block is cut into overlapped time segments that are staged
+ * through double-buffered device memory (H2D copy of segment i+1 overlaps K1/K2 of segment i and the D2H
+ * of segment i-1).  Synchronous: returns when `audio` is complete. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_process_host(
+    b200sdr_chain* chain, const void* hostInput, size_t numInputs, uint64_t firstSampleIndex, float* hostAudio,
+    size_t audioCapacity, size_t* numAudioOut);
+/* Staging segment size (input samples) used by b200sdr_chain_process_host; default 2^25. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_set_host_segment(b200sdr_chain* chain, size_t inputSamples);
+
+/* ---- introspection ------------------------------------------------------------------------------ */
+/* Kernels launched by this library since load (all streams); used by bench.py's gpu_launches. */
+B200SDR_EXPORT uint64_t b200sdr_launch_count(void);
+/* Name of the kernel variant K1 resolves to for this chain ("rows<MP=4,RPT=4,...>" or "direct"). */
+B200SDR_EXPORT const char* b200sdr_chain_variant(const b200sdr_chain* chain);
+B200SDR_EXPORT const char* b200sdr_version(void);
+
+#endif /* B200SDR_B200SDR_H */
