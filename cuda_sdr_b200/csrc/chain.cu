@@ -65,9 +65,9 @@ struct b200sdr_chain {
   // device-resident constants
   float* dTaps1 = nullptr;
   float* dTaps2 = nullptr;
-  float* dTapTable = nullptr;   // hT[D1][MP]
+  float* dTapTable = nullptr;   // hT[D1][TS]
   float2* dMixTable = nullptr;  // W[D1]
-  float2* dRotTable = nullptr;  // exp(j w m D1), m <= MP
+  float2* dRotTable = nullptr;  // exp(j w m D1), m <= TS
   FirRoute tableRoute {};       // route the tables were laid out for (aligned input)
   std::string variant;
 
@@ -166,22 +166,22 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
   // Tables of the rows kernel, evaluated in fp64 on the host (for a 16-byte-aligned input pointer).
   c->tableRoute = planFir(c->elem, false, nullptr, c->T1, c->D1, c->mod);
   if (ok && c->tableRoute.rows) {
-    const unsigned MP = c->tableRoute.MP, M = c->tableRoute.M, D = c->D1;
-    std::vector<float> hT(static_cast<size_t>(D) * MP, 0.0f);
+    const unsigned TS = c->tableRoute.TS, M = c->tableRoute.M, D = c->D1;
+    std::vector<float> hT(static_cast<size_t>(D) * TS, 0.0f);
     for (unsigned p = 0; p < D; p++)
       for (unsigned m = 0; m < M; m++) {
         const size_t j = static_cast<size_t>(m) * D + p;
-        if (j < c->T1) hT[static_cast<size_t>(p) * MP + m] = cfg->rf_taps[j] * (c->mix ? 1.0f : c->inScale);
+        if (j < c->T1) hT[static_cast<size_t>(p) * TS + m] = cfg->rf_taps[j] * (c->mix ? 1.0f : c->inScale);
       }
     ok = upload(hT.data(), hT.size() * sizeof(float), reinterpret_cast<void**>(&c->dTapTable));
     if (ok && c->mix) {
-      std::vector<float2> W(D), rot(MP + 1);
+      std::vector<float2> W(D), rot(TS + 1);
       for (unsigned p = 0; p < D; p++) {
         W[p] = hostPhasor(c->phaseStep * p);
         W[p].x *= c->inScale;
         W[p].y *= c->inScale;
       }
-      for (unsigned m = 0; m <= MP; m++) rot[m] = hostPhasor(c->phaseStep * (static_cast<uint64_t>(m) * D));
+      for (unsigned m = 0; m <= TS; m++) rot[m] = hostPhasor(c->phaseStep * (static_cast<uint64_t>(m) * D));
       ok = upload(W.data(), W.size() * sizeof(float2), reinterpret_cast<void**>(&c->dMixTable)) &&
            upload(rot.data(), rot.size() * sizeof(float2), reinterpret_cast<void**>(&c->dRotTable));
     }

@@ -15,31 +15,18 @@ namespace {
 
 using Kernel = void (*)(const FirParams);
 
-template <int ELEM, bool MIX>
-struct RowsTable {
-  // [MP index: 1,2,4,8][RPT index: low, high]
-  static Kernel get(int mpIdx, int rptIdx) {
-    static const Kernel table[4][2] = {
-        {rowsKernel<ELEM, MIX, 1, 1>, rowsKernel<ELEM, MIX, 1, 4>},
-        {rowsKernel<ELEM, MIX, 2, 1>, rowsKernel<ELEM, MIX, 2, 4>},
-        {rowsKernel<ELEM, MIX, 4, 1>, rowsKernel<ELEM, MIX, 4, 4>},
-        {rowsKernel<ELEM, MIX, 8, 1>, rowsKernel<ELEM, MIX, 8, 2>},
-    };
-    return table[mpIdx][rptIdx];
-  }
-};
+// rows kernels are instantiated in fir_rows_*.cu (one translation unit per element type / mixer flag so
+// that nvcc compiles them in parallel); [MP-1][RPT index: 1 row, high]
+Kernel rowsKernelFor(int elem, bool mix, unsigned MP, int rptIdx) {
+  const Kernel* table = elem == kElemInt8Complex ? (mix ? kRowsInt8Mix : kRowsInt8Plain) : (mix ? kRowsCf32Mix : kRowsCf32Plain);
+  return table[(MP - 1) * 2 + rptIdx];
+}
 
-constexpr int kRptHigh[4] = {4, 4, 4, 2};
 constexpr unsigned kMaxDynSmem = 200 * 1024;
 
 int envInt(const char* name, int fallback) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : fallback;
-}
-
-Kernel rowsKernelFor(int elem, bool mix, int mpIdx, int rptIdx) {
-  if (elem == kElemInt8Complex) return mix ? RowsTable<kElemInt8Complex, true>::get(mpIdx, rptIdx) : RowsTable<kElemInt8Complex, false>::get(mpIdx, rptIdx);
-  return mix ? RowsTable<kElemComplex, true>::get(mpIdx, rptIdx) : RowsTable<kElemComplex, false>::get(mpIdx, rptIdx);
 }
 
 template <bool STAGED>
@@ -70,16 +57,16 @@ FirRoute planFir(int elem, bool tapsComplex, const void* in, unsigned T, unsigne
   const unsigned es = elem == kElemInt8Complex ? 2u : 8u;
   const unsigned vec = 16u / es;
   if (D % vec != 0 || (reinterpret_cast<uintptr_t>(in) & 15u) != 0 || r.M > 8) return r;
-  r.mpIdx = r.M <= 1 ? 0 : r.M <= 2 ? 1 : r.M <= 4 ? 2 : 3;
-  r.MP = 1u << r.mpIdx;
+  r.MP = r.M;
+  r.TS = static_cast<unsigned>(tapStride(static_cast<int>(r.MP)));
   const int forcedRpt = envInt("B200SDR_RPT", 0);
   const unsigned fm = mod == kModFm ? 1u : 0u;
   for (int rptIdx = 1; rptIdx >= 0; rptIdx--) {
-    const unsigned rpt = rptIdx ? kRptHigh[r.mpIdx] : 1u;
+    const unsigned rpt = rptIdx ? rowsRptHigh(r.MP) : 1u;
     if (forcedRpt == 1 && rptIdx == 1) continue;
     const unsigned rowsPerTile = rpt * kRowsThreads;
     if (rowsPerTile <= r.M - 1 + fm) continue;
-    const RowsSmem lay = rowsSmemLayout(D, r.MP, r.M, rowsPerTile, es, fm != 0);
+    const RowsSmem lay = rowsSmemLayout(D, r.TS, r.M, rowsPerTile, es, fm != 0);
     // keep at least ~3 tiles resident per SM for the high-RPT variant so TMA latency hides behind compute
     const unsigned limit = rptIdx ? 72u * 1024u : kMaxDynSmem;
     if (lay.total > limit) continue;
@@ -102,7 +89,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
   if (route.rows) {
     prm.rowsPerTile = route.rowsPerTile;
     prm.outPerTile = route.outPerTile;
-    const Kernel k = rowsKernelFor(elem, mix, route.mpIdx, route.rptIdx);
+    const Kernel k = rowsKernelFor(elem, mix, route.MP, route.rptIdx);
     if (route.smemBytes > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
       if (e != cudaSuccess) return e;

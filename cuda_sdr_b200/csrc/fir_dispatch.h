@@ -12,8 +12,9 @@ struct FirParams;
 struct FirRoute {
   bool rows;      // true: rowsKernel; false: directKernel
   unsigned M;     // ceil(T / D)
-  unsigned MP;    // padded partial-sum count (1, 2, 4, 8)
-  int mpIdx, rptIdx;
+  unsigned MP;    // partial sums kept per row (= M, 1..8)
+  unsigned TS;    // row stride of the transposed tap table (next power of two of MP)
+  int rptIdx;
   unsigned rpt, rowsPerTile, outPerTile, smemBytes;
 };
 
@@ -21,5 +22,11 @@ FirRoute planFir(int elem, bool tapsComplex, const void* in, unsigned T, unsigne
 cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaStream_t stream);
 const char* firVariantName(int elem, bool tapsComplex, bool mix, const FirRoute& route, char* buf, size_t bufLen);
 uint64_t phaseStepOf(double frequency, double sampleRate);
+
+// rows per thread of the high-RPT variant for MP partial sums (register budget)
+constexpr unsigned rowsRptHigh(unsigned MP) { return MP <= 4 ? 4u : 2u; }
+
+using FirKernel = void (*)(const FirParams);
+extern const FirKernel kRowsInt8Mix[16], kRowsInt8Plain[16], kRowsCf32Mix[16], kRowsCf32Plain[16];
 
 }  // namespace b200sdr

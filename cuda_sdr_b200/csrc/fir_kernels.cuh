@@ -26,9 +26,9 @@ struct FirParams {
   const void* in;          // input elements (int8 pairs / float2 / float)
   void* out;               // float (AM/FM or real data) or float2
   const float* taps;       // raw device taps: T floats (real) or T float2 (complex); may be null if tables given
-  const float* tapTable;   // rows path: hT[D][MP], pre-scaled; null -> built from `taps` in the prologue
+  const float* tapTable;   // rows path: hT[D][tapStride(MP)], pre-scaled; null -> built from `taps` in the prologue
   const float2* mixTable;  // rows path: W[D] (already scaled by inScale); null -> computed from phaseStep
-  const float2* rotTable;  // rows path: exp(j*w*m*D), m <= MP; null -> computed from phaseStep
+  const float2* rotTable;  // rows path: exp(j*w*m*D), m <= tapStride(MP); null -> computed from phaseStep
   unsigned long long nOut;
   unsigned long long nIn;  // valid input elements starting at `in`
   unsigned long long firstIndex;  // absolute sample index of in[0] (mixer phase)
@@ -82,23 +82,30 @@ struct ElemTraits<kElemComplex> {
 
 constexpr int kRowsThreads = 128;
 
+// Row stride (floats) of the transposed tap table hT[p][.] for MP partial sums: next power of two.
+__host__ __device__ constexpr int tapStride(int MP) { return MP <= 1 ? 1 : MP <= 2 ? 2 : MP <= 4 ? 4 : 8; }
+
 template <int MP>
 __device__ __forceinline__ void loadTapRow(const float* hT, unsigned p, float (&h)[MP]) {
-  if constexpr (MP == 1) {
+  constexpr int TS = tapStride(MP);
+  if constexpr (TS == 1) {
     h[0] = hT[p];
-  } else if constexpr (MP == 2) {
+  } else if constexpr (TS == 2) {
     const float2 v = reinterpret_cast<const float2*>(hT)[p];
     h[0] = v.x;
     h[1] = v.y;
   } else {
+    float t[TS];
 #pragma unroll
-    for (int i = 0; i < MP / 4; i++) {
-      const float4 v = reinterpret_cast<const float4*>(hT)[p * (MP / 4) + i];
-      h[4 * i] = v.x;
-      h[4 * i + 1] = v.y;
-      h[4 * i + 2] = v.z;
-      h[4 * i + 3] = v.w;
+    for (int i = 0; i < TS / 4; i++) {
+      const float4 v = reinterpret_cast<const float4*>(hT)[p * (TS / 4) + i];
+      t[4 * i] = v.x;
+      t[4 * i + 1] = v.y;
+      t[4 * i + 2] = v.z;
+      t[4 * i + 3] = v.w;
     }
+#pragma unroll
+    for (int m = 0; m < MP; m++) h[m] = t[m];
   }
 }
 
@@ -106,16 +113,16 @@ __device__ __forceinline__ void loadTapRow(const float* hT, unsigned p, float (&
 struct RowsSmem {
   unsigned mixOff, rotOff, tapOff, tileOff, total;
 };
-__host__ __device__ inline RowsSmem rowsSmemLayout(unsigned D, unsigned MP, unsigned M, unsigned rowsPerTile, unsigned elemBytes, bool fm) {
+__host__ __device__ inline RowsSmem rowsSmemLayout(unsigned D, unsigned TS, unsigned M, unsigned rowsPerTile, unsigned elemBytes, bool fm) {
   RowsSmem s;
   unsigned off = 16;  // mbarrier
   s.mixOff = off;
   off += D * 8;
   s.rotOff = off;
-  off += (MP + 1) * 8;
+  off += (TS + 1) * 8;
   off = (off + 15u) & ~15u;
   s.tapOff = off;
-  off += D * MP * 4;
+  off += D * TS * 4;
   off = (off + 127u) & ~127u;
   s.tileOff = off;
   const unsigned tileBytes = rowsPerTile * D * elemBytes;
@@ -133,7 +140,8 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
   extern __shared__ __align__(128) unsigned char smem[];
 
   const unsigned D = prm.D, M = prm.M, NT = prm.rowsPerTile;
-  const RowsSmem lay = rowsSmemLayout(D, MP, M, NT, ES, prm.mod == kModFm);
+  constexpr int TS = tapStride(MP);
+  const RowsSmem lay = rowsSmemLayout(D, TS, M, NT, ES, prm.mod == kModFm);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   float2* W = reinterpret_cast<float2*>(smem + lay.mixOff);
   float2* rot = reinterpret_cast<float2*>(smem + lay.rotOff);
@@ -161,12 +169,12 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
   }
 
   // ---- tables ----------------------------------------------------------------------------------------
-  for (unsigned i = tid; i < D * MP; i += kRowsThreads) {
+  for (unsigned i = tid; i < D * TS; i += kRowsThreads) {
     float v;
     if (prm.tapTable) {
       v = prm.tapTable[i];
     } else {
-      const unsigned p = i / MP, m = i % MP;
+      const unsigned p = i / TS, m = i % TS;
       const unsigned j = m * D + p;
       v = (m < M && j < prm.T) ? prm.taps[j] * (MIX ? 1.0f : prm.inScale) : 0.0f;
     }
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
       }
       W[p] = w;
     }
-    if (tid <= MP) {
+    if (tid <= TS) {
       rot[tid] = prm.rotTable ? prm.rotTable[tid] : phasorOfTurns(prm.phaseStep * (static_cast<unsigned long long>(tid) * D));
     }
   }

@@ -63,7 +63,7 @@ def test_c2_am_chain(sdr, n):
     kw = c2_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=12345, what="C2")
-    assert chain.variant.startswith("rows<int8c,mix=1,MP=4"), chain.variant
+    assert chain.variant.startswith("rows<int8c,mix=1,MP=3"), chain.variant
 
 
 @pytest.mark.parametrize("n", [1 << 20, 654321])
@@ -71,7 +71,7 @@ def test_c3_wbfm_chain(sdr, n):
     kw = c3_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=99, what="C3")
-    assert chain.variant.startswith("rows<int8c,mix=1,MP=8"), chain.variant
+    assert chain.variant.startswith("rows<int8c,mix=1,MP=7"), chain.variant
 
 
 def test_none_mode_outputs_mixed_rf_samples_with_absolute_phase(sdr):
@@ -114,7 +114,9 @@ def test_empty_and_short_inputs(sdr):
         x = torch.zeros(2 * n, dtype=torch.int8, device=DEV)
         out = chain.process_device(x)
         assert out.numel() == orc.chain_num_outputs(n, 101, 40, 0, 129, 10)
-    assert chain.counts(101 + 40 * 129)[2] == 1
+    # first audio output: 129 demod samples + (D2-1) for the count rule, each RF output rule likewise
+    n1 = 101 - 1 + 40 * (129 - 1 + 10)
+    assert chain.counts(n1)[2] == 1 == orc.chain_num_outputs(n1, 101, 40, 0, 129, 10) and chain.counts(n1 - 1)[2] == 0
 
 
 def test_time_segments_concatenate_bit_exactly(sdr):

@@ -121,7 +121,7 @@ def test_fir_fc_vs_oracle(ops, T, D, n):
 @pytest.mark.parametrize("T,D,n", [(2, 2, 5), (129, 10, 50000), (273, 5, 40000), (31, 1, 1000), (1500, 4, 20000)])
 def test_fir_other_kinds_vs_oracle(ops, kind, T, D, n):
     rng = np.random.default_rng(T + D + len(kind))
-    taps = _cplx(rng, T) / np.sqrt(T) if kind[0] == "c" else (rng.standard_normal(T) / np.sqrt(T)).astype(np.float32)
+    taps = (_cplx(rng, T) / np.sqrt(T)).astype(np.complex64) if kind[0] == "c" else (rng.standard_normal(T) / np.sqrt(T)).astype(np.float32)
     x = _cplx(rng, n) if kind[1] == "c" else rng.standard_normal(n).astype(np.float32)
     got = ops.fir(kind, torch.from_numpy(np.ascontiguousarray(taps)).to(DEV), torch.from_numpy(x).to(DEV), D).cpu().numpy()
     assert_close(got, orc.fir(kind, taps, x, D), what=f"fir{kind.upper()} T={T} D={D}")
