@@ -1,0 +1,196 @@
+// ref_chain.cpp -- drives the int8 -> mix -> FIR -> demod -> audio-FIR chain through the REFERENCE'S PUBLIC API
+// (getFactoriesSingleton(), Filter::requestBuffer/commitBuffer/readOutput), node by node and in <= 1 MiB steps,
+// exactly the way /root/reference/src/applications/nbfm_test.cpp:256-354 drives it by hand.
+//
+// TEST INFRASTRUCTURE (oracle/).  build_ref.sh links this one source three ways:
+//   oracle/_ref/ref_chain_naive : reference host framework (compiled in place) + oracle/ref/gsdr_naive.cu
+//                                 = the "reference CUDA pipeline" baseline B1 of SURVEY.md section 8(d)
+//   oracle/_ref/ref_chain_b200  : reference host framework + THIS repo's libb200sdr.so as the gsdr library
+//                                 (drop-in proof at the gsdr boundary)
+//   oracle/_ref/ref_chain_ours  : THIS repo's libgpusdrpipeline.so (drop-in proof at the IFactories boundary)
+//
+// usage: ref_chain --fs HZ --freq HZ --mod am|fm [--dev HZ] --d1 N --taps1 F32FILE --d2 N --taps2 F32FILE
+//                  --in INT8FILE [--out F32FILE] [--repeat R] [--step BYTES] [--fused]
+// Prints one JSON line: samples, outputs, seconds, Msps.
+#include <cuComplex.h>
+#include <cuda_runtime.h>
+#include <gpusdrpipeline/Factories.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace std;
+
+static vector<char> readFile(const string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
+    fprintf(stderr, "cannot open %s\n", path.c_str());
+    exit(2);
+  }
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  vector<char> data(static_cast<size_t>(n));
+  if (n > 0 && fread(data.data(), 1, data.size(), f) != data.size()) {
+    fprintf(stderr, "short read on %s\n", path.c_str());
+    exit(2);
+  }
+  fclose(f);
+  return data;
+}
+
+static vector<float> readFloats(const string& path) {
+  const vector<char> raw = readFile(path);
+  vector<float> v(raw.size() / sizeof(float));
+  memcpy(v.data(), raw.data(), v.size() * sizeof(float));
+  return v;
+}
+
+struct Args {
+  double fs = 19.2e6, freq = 0, dev = 75e3;
+  string mod = "am", taps1, taps2, in, out;
+  size_t d1 = 1, d2 = 1, repeat = 1, step = 1 << 20;
+};
+
+static Args parse(int argc, char** argv) {
+  Args a;
+  for (int i = 1; i + 1 < argc; i += 2) {
+    const string k = argv[i], v = argv[i + 1];
+    if (k == "--fs") a.fs = atof(v.c_str());
+    else if (k == "--freq") a.freq = atof(v.c_str());
+    else if (k == "--dev") a.dev = atof(v.c_str());
+    else if (k == "--mod") a.mod = v;
+    else if (k == "--d1") a.d1 = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--d2") a.d2 = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--taps1") a.taps1 = v;
+    else if (k == "--taps2") a.taps2 = v;
+    else if (k == "--in") a.in = v;
+    else if (k == "--out") a.out = v;
+    else if (k == "--repeat") a.repeat = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--step") a.step = strtoull(v.c_str(), nullptr, 10);
+    else {
+      fprintf(stderr, "unknown argument %s\n", k.c_str());
+      exit(2);
+    }
+  }
+  if (a.taps1.empty() || a.taps2.empty() || a.in.empty()) {
+    fprintf(stderr, "--taps1, --taps2 and --in are required\n");
+    exit(2);
+  }
+  return a;
+}
+
+// requestBuffer(port, bytes) with a floor, so that a stage with nothing to emit this step still hands the
+// upstream node a valid (empty-range) buffer to append zero bytes to
+static Ref<IBuffer> request(Sink* sink, size_t port, size_t bytes) { return unwrap(sink->requestBuffer(port, bytes < 256 ? 256 : bytes)); }
+
+int main(int argc, char** argv) {
+  const Args a = parse(argc, argv);
+  gslogSetVerbosity(GSLOG_WARN);
+  const vector<char> input = readFile(a.in);
+  const vector<float> taps1 = readFloats(a.taps1), taps2 = readFloats(a.taps2);
+  const bool fm = a.mod == "fm";
+
+  ConstRef<IFactories> factories = unwrap(getFactoriesSingleton());
+  ConstRef<ICudaCommandQueue> queue = unwrap(factories->getCudaCommandQueueFactory()->create(0));
+  const float rfRate = static_cast<float>(a.fs);
+  const float demodRate = static_cast<float>(a.fs / static_cast<double>(a.d1));
+
+  ConstRef<Filter> hostToDevice = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyHostToDevice, queue));
+  ConstRef<Filter> int8ToFloat = unwrap(factories->getInt8ToFloatFactory()->createFilter(queue));
+  ConstRef<Source> cosine = unwrap(factories->getCosineSourceFactory()->createCosineSource(
+      SampleType_FloatComplex, rfRate, static_cast<float>(a.freq), queue));
+  ConstRef<Filter> multiply = unwrap(factories->getMultiplyFactory()->createFilter(queue));
+  ConstRef<Filter> rfFir = unwrap(factories->getFirFactory()->createFir(
+      SampleType_Float, SampleType_FloatComplex, a.d1, taps1.data(), taps1.size(), queue));
+  ConstRef<Filter> demod = unwrap(factories->getQuadDemodFactory()->createQuadDemod(
+      fm ? Modulation_Fm : Modulation_Am, demodRate, static_cast<float>(a.dev), queue));
+  ConstRef<Filter> audioFir = unwrap(factories->getFirFactory()->createFir(
+      SampleType_Float, SampleType_Float, a.d2, taps2.data(), taps2.size(), queue));
+  ConstRef<Filter> deviceToHost = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyDeviceToHost, queue));
+
+  ConstRef<IAllocator> pinned = unwrap(factories->getCudaAllocatorFactory()->createCudaAllocator(queue, 32, /*useHostMemory=*/true));
+  ConstRef<IBufferFactory> pinnedBuffers = unwrap(factories->createBufferFactory(pinned));
+  ConstRef<IBuffer> hostOut = unwrap(pinnedBuffers->createBuffer(a.step * 4));
+
+  vector<float> audio;
+  audio.reserve(input.size() / 2 / (a.d1 * a.d2) * a.repeat + 16);
+  IBuffer* out[1];
+  size_t totalSamples = 0;
+
+  const auto t0 = chrono::steady_clock::now();
+  for (size_t rep = 0; rep < a.repeat; rep++) {
+    for (size_t pos = 0; pos < input.size();) {
+      const size_t step = input.size() - pos < a.step ? input.size() - pos : a.step;
+
+      Ref<IBuffer> staged = request(hostToDevice, 0, step);  // pinned host memory (CudaMemcpyFilter.cpp:42-47)
+      memcpy(staged->writePtr(), input.data() + pos, step);   // stands in for HackrfSource::readOutput
+      THROW_IF_ERR(hostToDevice->commitBuffer(0, step));
+      pos += step;
+      totalSamples += step / 2;
+
+      Ref<IBuffer> raw = request(int8ToFloat, 0, hostToDevice->getAlignedOutputDataSize(0));
+      out[0] = raw.get();
+      THROW_IF_ERR(hostToDevice->readOutput(out, 1));
+      THROW_IF_ERR(int8ToFloat->commitBuffer(0, raw->range()->used()));
+
+      const size_t rfBytes = int8ToFloat->getAlignedOutputDataSize(0);
+      Ref<IBuffer> rfIn = request(multiply, 0, rfBytes);
+      Ref<IBuffer> loIn = request(multiply, 1, rfBytes);
+      out[0] = rfIn.get();
+      // numPorts = 0: the reference's guard at Int8ToFloat.cpp:81 (`0 == portCount`) rejects the normal call with
+      // one port; passing 0 is the only form its own implementation accepts.  It still writes out[0].
+      THROW_IF_ERR(int8ToFloat->readOutput(out, 0));
+      THROW_IF_ERR(multiply->commitBuffer(0, rfIn->range()->used()));
+      out[0] = loIn.get();
+      THROW_IF_ERR(cosine->readOutput(out, 1));
+      THROW_IF_ERR(multiply->commitBuffer(1, loIn->range()->used()));
+
+      Ref<IBuffer> firIn = request(rfFir, 0, multiply->getAlignedOutputDataSize(0));
+      out[0] = firIn.get();
+      THROW_IF_ERR(multiply->readOutput(out, 1));
+      THROW_IF_ERR(rfFir->commitBuffer(0, firIn->range()->used()));
+
+      Ref<IBuffer> demodIn = request(demod, 0, rfFir->getAlignedOutputDataSize(0));
+      out[0] = demodIn.get();
+      THROW_IF_ERR(rfFir->readOutput(out, 1));
+      THROW_IF_ERR(demod->commitBuffer(0, demodIn->range()->used()));
+
+      Ref<IBuffer> audioIn = request(audioFir, 0, demod->getAlignedOutputDataSize(0));
+      out[0] = audioIn.get();
+      THROW_IF_ERR(demod->readOutput(out, 1));
+      THROW_IF_ERR(audioFir->commitBuffer(0, audioIn->range()->used()));
+
+      Ref<IBuffer> d2hIn = request(deviceToHost, 0, audioFir->getAlignedOutputDataSize(0));
+      out[0] = d2hIn.get();
+      THROW_IF_ERR(audioFir->readOutput(out, 1));
+      THROW_IF_ERR(deviceToHost->commitBuffer(0, d2hIn->range()->used()));
+
+      hostOut->range()->clearRange();
+      out[0] = hostOut.get();
+      THROW_IF_ERR(deviceToHost->readOutput(out, 1));
+      cudaSetDevice(queue->cudaDevice());
+      cudaStreamSynchronize(queue->cudaStream());  // nbfm_test.cpp:346-347
+      const size_t got = hostOut->range()->used() / sizeof(float);
+      const float* p = hostOut->readPtr<float>();
+      audio.insert(audio.end(), p, p + got);
+    }
+  }
+  const double seconds = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+
+  if (!a.out.empty()) {
+    FILE* f = fopen(a.out.c_str(), "wb");
+    if (!f || fwrite(audio.data(), sizeof(float), audio.size(), f) != audio.size()) {
+      fprintf(stderr, "cannot write %s\n", a.out.c_str());
+      return 2;
+    }
+    fclose(f);
+  }
+  printf("{\"samples\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, \"repeat\": %zu}\n",
+         totalSamples, audio.size(), seconds, static_cast<double>(totalSamples) / seconds / 1e6, a.step, a.repeat);
+  return 0;
+}

@@ -1,0 +1,24 @@
+#!/bin/bash
+# One GPU visit: parity tests, the bench line, the ncu launch list and one --set full capture of K1/K2.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+# Everything lands in gpurun_out/<tag>_*; summarise with tools/ncu_summary.py into profiles/.
+set -u
+TAG=${1:-run}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
+tail -3 $OUT/${TAG}_pytest.log
+python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+echo "bench rc=$?"
+cat $OUT/${TAG}_bench.json
+BENCH_SHORT="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu"
+$BENCH_SHORT > $OUT/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:b200sdr -s 6 -c 10 --csv --log-file $OUT/${TAG}_launches.csv \
+    $BENCH_SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:b200sdr -s 6 -c 2 \
+    -f -o $OUT/${TAG}_prof $BENCH_SHORT > $OUT/${TAG}_ncu_full.log 2>&1
+echo "ncu full rc=$?"
+ls -la $OUT | tail -20
