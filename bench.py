@@ -39,8 +39,11 @@ UNIT = "Msps"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup-seconds", type=float, default=0.5,
+                    help="keep running untimed warm-up steps until this much wall time has passed (a step is ~0.2 ms; "
+                         "the SM clock needs far longer than 3 steps to leave its idle state)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--log2-block", type=int, default=LOG2_BLOCK, help="log2 of input samples per GPU per step")
     ap.add_argument("--workload", choices=["am", "wbfm"], default="am")
@@ -262,8 +265,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warm_steps = 0
+    t_warm = time.perf_counter()
+    while warm_steps < max(args.warmup, 3) or time.perf_counter() - t_warm < args.warmup_seconds:
         step()
+        warm_steps += 1
+        if warm_steps % 16 == 0:
+            torch.cuda.synchronize()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -319,7 +327,7 @@ def run_ours(args):
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm_steps, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, wl, {"k1_variant": chain.variant}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

@@ -66,6 +66,23 @@ __device__ __forceinline__ void storeDemod(int mod, void* out, unsigned long lon
   }
 }
 
+// Packed FP32 (FFMA2 / FMUL2 / FADD2 on sm_100a): one issue slot carries two FMAs, and the scalar operand is
+// broadcast by the instruction itself (FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2).  The rows kernel is bound by
+// instruction issue, not by the FMA pipe, so every per-sample operation works on an (I, Q) register pair.
+__device__ __forceinline__ float2 axpy2(float a, float2 x, float2 y) { return __ffma2_rn(make_float2(a, a), x, y); }
+__device__ __forceinline__ float2 scale2(float a, float2 x) { return __fmul2_rn(make_float2(a, a), x); }
+// z * w with w given as (wx, wy, -wy, wx): z.x*(wx, wy) + z.y*(-wy, wx)
+__device__ __forceinline__ float2 cmulPacked(float2 z, float4 w) {
+  return axpy2(z.y, make_float2(w.z, w.w), scale2(z.x, make_float2(w.x, w.y)));
+}
+// Two (I, Q) samples packed as four int8 in one word (already XORed with 0x80808080) -> two exact float pairs
+__device__ __forceinline__ void biasedWordToPairs(uint32_t w, float2& z0, float2& z1) {
+  constexpr uint32_t kMagic = 0x4B000000u;  // 2^23
+  const float2 bias = make_float2(-8388736.0f, -8388736.0f);  // -(2^23 + 128)
+  z0 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, kMagic, 0x7650)), __uint_as_float(__byte_perm(w, kMagic, 0x7651))), bias);
+  z1 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, kMagic, 0x7652)), __uint_as_float(__byte_perm(w, kMagic, 0x7653))), bias);
+}
+
 // ------------------------------------------------------------------------------------------------
 // rows kernel
 // ------------------------------------------------------------------------------------------------
@@ -117,7 +134,7 @@ __host__ __device__ inline RowsSmem rowsSmemLayout(unsigned D, unsigned TS, unsi
   RowsSmem s;
   unsigned off = 16;  // mbarrier
   s.mixOff = off;
-  off += D * 8;
+  off += D * 16;  // (wx, wy, -wy, wx) per phase
   s.rotOff = off;
   off += (TS + 1) * 8;
   off = (off + 15u) & ~15u;
@@ -143,7 +160,7 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
   constexpr int TS = tapStride(MP);
   const RowsSmem lay = rowsSmemLayout(D, TS, M, NT, ES, prm.mod == kModFm);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  float2* W = reinterpret_cast<float2*>(smem + lay.mixOff);
+  float4* W = reinterpret_cast<float4*>(smem + lay.mixOff);  // (wx, wy, -wy, wx): both operand pairs of the packed complex multiply
   float2* rot = reinterpret_cast<float2*>(smem + lay.rotOff);
   float* hT = reinterpret_cast<float*>(smem + lay.tapOff);
   unsigned char* tile = smem + lay.tileOff;
@@ -190,7 +207,7 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
         w.x *= prm.inScale;
         w.y *= prm.inScale;
       }
-      W[p] = w;
+      W[p] = make_float4(w.x, w.y, -w.y, w.x);
     }
     if (tid <= TS) {
       rot[tid] = prm.rotTable ? prm.rotTable[tid] : phasorOfTurns(prm.phaseStep * (static_cast<unsigned long long>(tid) * D));
@@ -218,11 +235,18 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
 
     if constexpr (ELEM == kElemInt8Complex) {
 #pragma unroll
+      for (int i = 0; i < RPT; i++) {
+        v[i].x ^= 0x80808080u;
+        v[i].y ^= 0x80808080u;
+        v[i].z ^= 0x80808080u;
+        v[i].w ^= 0x80808080u;
+      }
+#pragma unroll
       for (int s = 0; s < 4; s++) {  // word s holds samples p+2s and p+2s+1 as I,Q,I,Q bytes
         float h0[MP], h1[MP];
         loadTapRow<MP>(hT, p + 2 * s, h0);
         loadTapRow<MP>(hT, p + 2 * s + 1, h1);
-        float2 w0, w1;
+        float4 w0, w1;
         if constexpr (MIX) {
           w0 = W[p + 2 * s];
           w1 = W[p + 2 * s + 1];
@@ -230,19 +254,16 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
           const uint32_t word = s == 0 ? v[i].x : s == 1 ? v[i].y : s == 2 ? v[i].z : v[i].w;
-          float a, b, c, d;
-          int8x4ToFloat(word, a, b, c, d);
-          float2 z0 = make_float2(a, b), z1 = make_float2(c, d);
+          float2 z0, z1;
+          biasedWordToPairs(word, z0, z1);
           if constexpr (MIX) {
-            z0 = cmulf(z0, w0);
-            z1 = cmulf(z1, w1);
+            z0 = cmulPacked(z0, w0);
+            z1 = cmulPacked(z1, w1);
           }
 #pragma unroll
           for (int m = 0; m < MP; m++) {
-            acc[i][m].x = fmaf(h0[m], z0.x, acc[i][m].x);
-            acc[i][m].y = fmaf(h0[m], z0.y, acc[i][m].y);
-            acc[i][m].x = fmaf(h1[m], z1.x, acc[i][m].x);
-            acc[i][m].y = fmaf(h1[m], z1.y, acc[i][m].y);
+            acc[i][m] = axpy2(h0[m], z0, acc[i][m]);
+            acc[i][m] = axpy2(h1[m], z1, acc[i][m]);
           }
         }
       }
@@ -250,7 +271,7 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
       float h0[MP], h1[MP];
       loadTapRow<MP>(hT, p, h0);
       loadTapRow<MP>(hT, p + 1, h1);
-      float2 w0, w1;
+      float4 w0, w1;
       if constexpr (MIX) {
         w0 = W[p];
         w1 = W[p + 1];
@@ -260,15 +281,13 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
         float2 z0 = make_float2(__uint_as_float(v[i].x), __uint_as_float(v[i].y));
         float2 z1 = make_float2(__uint_as_float(v[i].z), __uint_as_float(v[i].w));
         if constexpr (MIX) {
-          z0 = cmulf(z0, w0);
-          z1 = cmulf(z1, w1);
+          z0 = cmulPacked(z0, w0);
+          z1 = cmulPacked(z1, w1);
         }
 #pragma unroll
         for (int m = 0; m < MP; m++) {
-          acc[i][m].x = fmaf(h0[m], z0.x, acc[i][m].x);
-          acc[i][m].y = fmaf(h0[m], z0.y, acc[i][m].y);
-          acc[i][m].x = fmaf(h1[m], z1.x, acc[i][m].x);
-          acc[i][m].y = fmaf(h1[m], z1.y, acc[i][m].y);
+          acc[i][m] = axpy2(h0[m], z0, acc[i][m]);
+          acc[i][m] = axpy2(h1[m], z1, acc[i][m]);
         }
       }
     }

@@ -13,12 +13,13 @@ tail -3 $OUT/${TAG}_pytest.log
 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$?"
 cat $OUT/${TAG}_bench.json
-BENCH_SHORT="python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu"
+BENCH_SHORT="python bench.py --steps 5 --warmup 3 --warmup-seconds 0 --skip-e2e --skip-cpu"
+KERNELS='rowsKernel|directKernel|chainKernel|audioKernel|channelKernel'
 $BENCH_SHORT > $OUT/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:b200sdr -s 6 -c 10 --csv --log-file $OUT/${TAG}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$KERNELS" -s 6 -c 10 --csv --log-file $OUT/${TAG}_launches.csv \
     $BENCH_SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:b200sdr -s 6 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 6 -c 2 \
     -f -o $OUT/${TAG}_prof $BENCH_SHORT > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT | tail -20
