@@ -67,6 +67,7 @@ B200SDR_SYMBOLS = {
     "b200sdr_chain_segment": (u32, [vp, sz, sz, sz, psz, psz, psz, psz]),
     "b200sdr_chain_rf_stage": (u32, [vp, vp, sz, u64, vp, sz, stream_t]),
     "b200sdr_chain_audio_stage": (u32, [vp, vp, vp, sz, stream_t]),
+    "b200sdr_chain_run": (u32, [vp, vp, sz, u64, vp, vp, sz, stream_t]),
     "b200sdr_chain_process_device": (u32, [vp, vp, sz, u64, vp, vp, sz, psz, stream_t]),
     "b200sdr_chain_process_host": (u32, [vp, vp, sz, u64, vp, sz, psz]),
     "b200sdr_chain_set_host_segment": (u32, [vp, sz]),

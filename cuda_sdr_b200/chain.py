@@ -120,6 +120,23 @@ class Chain:
         N.check_status(st, "b200sdr_chain_audio_stage")
         return out
 
+    def run(self, x: torch.Tensor, n_audio: int, first_index: int = 0, out: torch.Tensor | None = None,
+            scratch: torch.Tensor | None = None, n_in: int | None = None) -> torch.Tensor:
+        """The whole chain producing exactly n_audio outputs (one persistent kernel when the shape allows)."""
+        assert x.is_cuda and x.is_contiguous()
+        n_in = self._num_inputs(x) if n_in is None else n_in
+        out = torch.empty(max(n_audio, 1), dtype=self._out_dtype(), device=x.device) if out is None else out
+        if scratch is None and self.T2 and self.modulation != NONE and not self.fused:
+            scratch = torch.empty(max((n_audio - 1) * self.audio_decim + self.T2, 1), dtype=torch.float32, device=x.device)
+        st = _lib.b200sdr_chain_run(self._h, x.data_ptr(), n_in, first_index, None if scratch is None else scratch.data_ptr(),
+                                    out.data_ptr(), n_audio, torch.cuda.current_stream(x.device).cuda_stream)
+        N.check_status(st, "b200sdr_chain_run")
+        return out[:n_audio]
+
+    @property
+    def fused(self) -> bool:
+        return self.variant.startswith("chain<")
+
     def process_device(self, x: torch.Tensor, first_index: int = 0, out: torch.Tensor | None = None,
                        scratch: torch.Tensor | None = None) -> torch.Tensor:
         """K1 + K2 over one device-resident block; returns the final outputs (a view of `out`)."""

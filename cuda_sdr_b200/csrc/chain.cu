@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include "chain_dispatch.h"
+#include "chain_kernels.cuh"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
 
@@ -69,6 +71,7 @@ struct b200sdr_chain {
   float2* dMixTable = nullptr;  // W[D1]
   float2* dRotTable = nullptr;  // exp(j w m D1), m <= TS
   FirRoute tableRoute {};       // route the tables were laid out for (aligned input)
+  ChainPlan fusedPlan {};       // fused persistent kernel (AM/FM with an audio FIR, aligned input), if the shape allows
   std::string variant;
 
   // host-buffer path
@@ -190,8 +193,15 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
     b200sdr_chain_destroy(c);
     return st;
   }
-  char buf[160];
-  c->variant = firVariantName(c->elem, false, c->mix, c->tableRoute, buf, sizeof(buf));
+  char buf[256];
+  if (c->hasAudioFir() && c->tableRoute.rows) {
+    c->fusedPlan = planChain(c->elem, c->mix, nullptr, c->T1, c->D1, c->mod, c->T2, c->D2, c->device);
+  }
+  if (c->fusedPlan.fused) {
+    c->variant = chainVariantName(c->elem, c->mix, c->fusedPlan, buf, sizeof(buf));
+  } else {
+    c->variant = firVariantName(c->elem, false, c->mix, c->tableRoute, buf, sizeof(buf));
+  }
   *chainOut = c;
   return B200SDR_OK;
 }
@@ -284,30 +294,58 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_audio_stage(
   return B200SDR_OK;
 }
 
+B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
+    b200sdr_chain* c, const void* input, size_t numInputs, uint64_t firstSampleIndex, float* demodScratch, float* audio,
+    size_t numAudio, cudaStream_t stream) {
+  if (!c) return fail(B200SDR_INVALID_ARGUMENT, "chain is null");
+  if (numAudio == 0) return B200SDR_OK;
+  if (!input || !audio) return fail(B200SDR_INVALID_ARGUMENT, "input/audio is null");
+  if (numInputs < (numAudio - 1) * c->stride() + c->window())
+    return fail(B200SDR_OUT_OF_RANGE, "numAudio outputs need more input samples than numInputs");
+  if (!c->hasAudioFir()) return b200sdr_chain_rf_stage(c, input, numInputs, firstSampleIndex, audio, numAudio, stream);
+
+  if (c->fusedPlan.fused && (reinterpret_cast<uintptr_t>(input) & 15u) == 0) {
+    // one persistent kernel: the demodulated stream stays in shared memory (demodScratch is not touched)
+    DeviceGuard guard(c->device);
+    if (guard.status != cudaSuccess) return cudaFail(guard.status, "cudaSetDevice");
+    ChainParams prm {};
+    prm.in = input;
+    prm.out = audio;
+    prm.tapTable = c->dTapTable;
+    prm.mixTable = c->dMixTable;
+    prm.rotTable = c->dRotTable;
+    prm.taps2 = c->dTaps2;
+    prm.nIn = numInputs;
+    prm.nAudio = numAudio;
+    prm.T1 = c->T1;
+    prm.D1 = c->D1;
+    prm.T2 = c->T2;
+    prm.D2 = c->D2;
+    prm.mod = c->mod;
+    prm.gain = c->fmGain;
+    CUDA_OR_RETURN(launchChain(c->elem, c->mix, c->fusedPlan, prm, stream));
+    return B200SDR_OK;
+  }
+  // two kernels: K1 writes the demodulated stream to demodScratch, K2 (audio FIR) reads it back
+  if (!demodScratch) return fail(B200SDR_INVALID_ARGUMENT, "demodScratch is null and this shape/alignment cannot take the fused kernel");
+  const size_t nDemod = (numAudio - 1) * static_cast<size_t>(c->D2) + c->T2;
+  b200sdr_status st = b200sdr_chain_rf_stage(c, input, numInputs, firstSampleIndex, demodScratch, nDemod, stream);
+  if (st != B200SDR_OK) return st;
+  return b200sdr_chain_audio_stage(c, demodScratch, audio, numAudio, stream);
+}
+
 B200SDR_EXPORT b200sdr_status b200sdr_chain_process_device(
     b200sdr_chain* c, const void* input, size_t numInputs, uint64_t firstSampleIndex, float* demodScratch,
     float* audio, size_t audioCapacity, size_t* numAudioOut, cudaStream_t stream) {
   if (numAudioOut) *numAudioOut = 0;
   if (!c) return fail(B200SDR_INVALID_ARGUMENT, "chain is null");
   size_t nRf, nDemod, nAudio;
-  b200sdr_chain_counts(c, numInputs, &nRf, &nDemod, &nAudio);
-  if (c->hasAudioFir()) {
-    if (nAudio > audioCapacity) nAudio = audioCapacity;  // produce what fits; nothing is skipped (caller keeps input)
-    if (nAudio == 0) return B200SDR_OK;
-    nDemod = (nAudio - 1) * static_cast<size_t>(c->D2) + c->T2;
-    if (!demodScratch) return fail(B200SDR_INVALID_ARGUMENT, "demodScratch is null");
-    b200sdr_status st = b200sdr_chain_rf_stage(c, input, numInputs, firstSampleIndex, demodScratch, nDemod, stream);
-    if (st != B200SDR_OK) return st;
-    st = b200sdr_chain_audio_stage(c, demodScratch, audio, nAudio, stream);
-    if (st != B200SDR_OK) return st;
-  } else {
-    if (nDemod > audioCapacity) nDemod = audioCapacity;
-    nAudio = nDemod;
-    const b200sdr_status st = b200sdr_chain_rf_stage(c, input, numInputs, firstSampleIndex, audio, nDemod, stream);
-    if (st != B200SDR_OK) return st;
-  }
-  if (numAudioOut) *numAudioOut = nAudio;
-  return B200SDR_OK;
+  b200sdr_chain_counts(c, numInputs, &nRf, &nDemod, &nAudio);  // the reference's count rules (Fir.cpp:141-187)
+  if (nAudio > audioCapacity) nAudio = audioCapacity;          // produce what fits; nothing is skipped (caller keeps input)
+  if (nAudio == 0) return B200SDR_OK;
+  const b200sdr_status st = b200sdr_chain_run(c, input, numInputs, firstSampleIndex, demodScratch, audio, nAudio, stream);
+  if (st == B200SDR_OK && numAudioOut) *numAudioOut = nAudio;
+  return st;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -389,13 +427,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_process_host(
     CUDA_OR_RETURN(cudaMemcpyAsync(c->slotIn[slot], hostBytes + in0 * c->elemBytes(), inCount * c->elemBytes(), cudaMemcpyHostToDevice, c->h2d));
     CUDA_OR_RETURN(cudaEventRecord(c->copied[slot], c->h2d));
     CUDA_OR_RETURN(cudaStreamWaitEvent(c->compute, c->copied[slot], 0));
-    if (c->hasAudioFir()) {
-      const size_t demodCount = (count - 1) * c->D2 + c->T2;
-      st = b200sdr_chain_rf_stage(c, c->slotIn[slot], inCount, firstSampleIndex + in0, c->slotDemod[slot], demodCount, c->compute);
-      if (st == B200SDR_OK) st = b200sdr_chain_audio_stage(c, c->slotDemod[slot], c->slotAudio[slot], count, c->compute);
-    } else {
-      st = b200sdr_chain_rf_stage(c, c->slotIn[slot], inCount, firstSampleIndex + in0, c->slotAudio[slot], count, c->compute);
-    }
+    st = b200sdr_chain_run(c, c->slotIn[slot], inCount, firstSampleIndex + in0, c->slotDemod[slot], c->slotAudio[slot], count, c->compute);
     if (st != B200SDR_OK) return st;
     CUDA_OR_RETURN(cudaEventRecord(c->computed[slot], c->compute));
     CUDA_OR_RETURN(cudaStreamWaitEvent(c->d2h, c->computed[slot], 0));

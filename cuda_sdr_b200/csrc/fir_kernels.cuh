@@ -83,6 +83,33 @@ __device__ __forceinline__ void biasedWordToPairs(uint32_t w, float2& z0, float2
   z1 = __fadd2_rn(make_float2(__uint_as_float(__byte_perm(w, kMagic, 0x7652)), __uint_as_float(__byte_perm(w, kMagic, 0x7653))), bias);
 }
 
+// Sign-extending byte extraction + I2FP: int8 -> float entirely on the ALU pipe, leaving the FMA pipe (the busiest
+// unit of the main loop) to the mixer and the taps.  prmt's selector nibbles with bit 3 set replicate the sign of the
+// selected byte; __byte_perm masks that bit off, hence the inline PTX.
+template <unsigned SEL>
+__device__ __forceinline__ float signedByteToFloat(uint32_t w) {
+  int v;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(v) : "r"(w), "n"(SEL));
+  return __int2float_rn(v);
+}
+__device__ __forceinline__ void wordToPairsAlu(uint32_t w, float2& z0, float2& z1) {
+  z0 = make_float2(signedByteToFloat<0x8880u>(w), signedByteToFloat<0x9991u>(w));
+  z1 = make_float2(signedByteToFloat<0xAAA2u>(w), signedByteToFloat<0xBBB3u>(w));
+}
+
+// CONV = 0: magic-number route (PRMT + FADD2, needs the XOR);  CONV = 1: sign-extend + I2FP (ALU pipe only)
+template <int CONV>
+__device__ __forceinline__ void convertWord(uint32_t w, float2& z0, float2& z1) {
+  if constexpr (CONV == 0) {
+    biasedWordToPairs(w ^ 0x80808080u, z0, z1);
+  } else {
+    wordToPairsAlu(w, z0, z1);
+  }
+}
+#ifndef B200SDR_ROWS_CONV
+#define B200SDR_ROWS_CONV 1
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // rows kernel
 // ------------------------------------------------------------------------------------------------
@@ -235,13 +262,6 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
 
     if constexpr (ELEM == kElemInt8Complex) {
 #pragma unroll
-      for (int i = 0; i < RPT; i++) {
-        v[i].x ^= 0x80808080u;
-        v[i].y ^= 0x80808080u;
-        v[i].z ^= 0x80808080u;
-        v[i].w ^= 0x80808080u;
-      }
-#pragma unroll
       for (int s = 0; s < 4; s++) {  // word s holds samples p+2s and p+2s+1 as I,Q,I,Q bytes
         float h0[MP], h1[MP];
         loadTapRow<MP>(hT, p + 2 * s, h0);
@@ -255,7 +275,7 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
         for (int i = 0; i < RPT; i++) {
           const uint32_t word = s == 0 ? v[i].x : s == 1 ? v[i].y : s == 2 ? v[i].z : v[i].w;
           float2 z0, z1;
-          biasedWordToPairs(word, z0, z1);
+          convertWord<B200SDR_ROWS_CONV>(word, z0, z1);
           if constexpr (MIX) {
             z0 = cmulPacked(z0, w0);
             z1 = cmulPacked(z1, w1);

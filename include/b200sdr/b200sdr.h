@@ -98,7 +98,14 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_rf_stage(
 /* Stage K2: audio FIR (float taps, float data, decimating). */
 B200SDR_EXPORT b200sdr_status b200sdr_chain_audio_stage(
     b200sdr_chain* chain, const float* demod, float* audio, size_t numAudio, cudaStream_t stream);
-/* K1 + K2 over one block.  `demodScratch` must hold numDemod floats (see b200sdr_chain_counts).
+/* The whole chain over one block, producing EXACTLY numAudio final outputs (time-segment sharding, host staging).
+ * Needs numInputs >= (numAudio-1)*stride + window.  When the shape allows (AM/FM with an audio FIR, D1 a multiple
+ * of the 16-byte vector, <= 8 taps per decimation phase, 16-byte aligned input) this is ONE persistent kernel and
+ * `demodScratch` is not touched (may be NULL); otherwise K1 + K2 through demodScratch. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
+    b200sdr_chain* chain, const void* input, size_t numInputs, uint64_t firstSampleIndex, float* demodScratch,
+    float* audio, size_t numAudio, cudaStream_t stream);
+/* Same, with the number of outputs given by the reference's count rules (b200sdr_chain_counts).  `demodScratch` must hold numDemod floats (see b200sdr_chain_counts).
  * *numAudioOut receives the number of final outputs written to `audio`. */
 B200SDR_EXPORT b200sdr_status b200sdr_chain_process_device(
     b200sdr_chain* chain, const void* input, size_t numInputs, uint64_t firstSampleIndex, float* demodScratch,

@@ -1,5 +1,6 @@
-"""GPU parity of the fused chain (K1 = convert+mix+FIR+demod, K2 = audio FIR), called through the
-b200sdr C-ABI, against the fp64 CPU oracle; plus size-independent properties at BASELINE sizes."""
+"""GPU parity of the chain -- the fused persistent kernel (chainKernel) and the two-kernel path (K1 =
+convert+mix+FIR+demod, K2 = audio FIR) -- called through the b200sdr C-ABI, against the fp64 CPU oracle; plus
+size-independent properties at BASELINE sizes."""
 import numpy as np
 import pytest
 import torch
@@ -63,7 +64,7 @@ def test_c2_am_chain(sdr, n):
     kw = c2_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=12345, what="C2")
-    assert chain.variant.startswith("rows<int8c,mix=1,MP=3"), chain.variant
+    assert chain.variant.startswith(("chain<int8c,mix=1,MP=3", "rows<int8c,mix=1,MP=3")), chain.variant
 
 
 @pytest.mark.parametrize("n", [1 << 20, 654321])
@@ -71,7 +72,7 @@ def test_c3_wbfm_chain(sdr, n):
     kw = c3_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=99, what="C3")
-    assert chain.variant.startswith("rows<int8c,mix=1,MP=7"), chain.variant
+    assert chain.variant.startswith(("chain<int8c,mix=1,MP=7", "rows<int8c,mix=1,MP=7")), chain.variant
 
 
 def test_none_mode_outputs_mixed_rf_samples_with_absolute_phase(sdr):
@@ -119,7 +120,8 @@ def test_empty_and_short_inputs(sdr):
     assert chain.counts(n1)[2] == 1 == orc.chain_num_outputs(n1, 101, 40, 0, 129, 10) and chain.counts(n1 - 1)[2] == 0
 
 
-def test_time_segments_concatenate_bit_exactly(sdr):
+def test_time_segments_concatenate_bit_exactly(sdr, monkeypatch):
+    monkeypatch.setenv("B200SDR_FUSED", "1")
     """Outputs are a pure function of the absolute sample index: overlapped time segments (the
     multi-GPU and host-staging decomposition) must reproduce the one-shot result bit for bit."""
     kw = c3_spec(sdr)
@@ -128,17 +130,53 @@ def test_time_segments_concatenate_bit_exactly(sdr):
     x = torch.from_numpy(sdr.synth.int8_iq(n)).to(DEV)
     whole = chain.process_device(x)
     n_audio = whole.numel()
+    assert chain.fused
     for parts in (2, 3, 8):
         outs = []
         for i in range(parts):
             a0, cnt, i0, icnt = chain.segment(n_audio, parts, i)
             seg = x[2 * i0: 2 * (i0 + icnt)]
-            n_demod = (cnt - 1) * chain.audio_decim + chain.T2
-            demod = chain.rf_stage(seg, n_demod, i0, n_in=icnt)
-            outs.append(chain.audio_stage(demod, cnt))
+            outs.append(chain.run(seg, cnt, i0, n_in=icnt))
         cat = torch.cat(outs)
         assert cat.numel() == n_audio
         assert torch.equal(cat.view(torch.int32), whole.view(torch.int32)), f"parts={parts}"
+
+
+def test_two_kernel_path_segments_concatenate_bit_exactly(sdr, monkeypatch):
+    monkeypatch.setenv("B200SDR_FUSED", "0")
+    kw = c3_spec(sdr)
+    chain = sdr.Chain(**kw)
+    assert not chain.fused
+    n = 1 << 19
+    x = torch.from_numpy(sdr.synth.int8_iq(n)).to(DEV)
+    whole = chain.process_device(x)
+    n_audio = whole.numel()
+    outs = []
+    for i in range(3):
+        a0, cnt, i0, icnt = chain.segment(n_audio, 3, i)
+        seg = x[2 * i0: 2 * (i0 + icnt)]
+        demod = chain.rf_stage(seg, (cnt - 1) * chain.audio_decim + chain.T2, i0, n_in=icnt)
+        outs.append(chain.audio_stage(demod, cnt))
+    assert torch.equal(torch.cat(outs).view(torch.int32), whole.view(torch.int32))
+
+
+@pytest.mark.parametrize("env", [
+    {"B200SDR_FUSED": "0"}, {"B200SDR_FUSED": "1"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "2"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "4"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "1"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "2", "B200SDR_CHAIN_CTAS": "1"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_CONV": "0"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_CONV": "1"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_PARTS": "1"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_PARTS": "8"},
+])
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_every_kernel_variant_matches_the_oracle(sdr, monkeypatch, env, which):
+    """Tile shape, ring depth, conversion route and audio split are tuning knobs: each must give the same
+    results (to the north-star tolerance) and the same counts."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    kw = c2_spec(sdr) if which == "c2" else c3_spec(sdr)
+    x = sdr.synth.int8_iq(400000 + 17, seed=11)
+    chain, _ = check_chain(sdr, kw, x, n0=4242, what=f"{which} {env}")
+    assert chain.fused == (env.get("B200SDR_FUSED") == "1")
 
 
 def test_host_path_equals_device_path(sdr):
