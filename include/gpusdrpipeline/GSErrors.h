@@ -1,0 +1,5 @@
+/* Forwarding header: the reference's include path for declarations that live in <gpusdrpipeline/abi/core.h>. */
+#ifndef GPUSDRPIPELINE_FWD_GSERRORS_H
+#define GPUSDRPIPELINE_FWD_GSERRORS_H
+#include <gpusdrpipeline/abi/core.h>
+#endif

@@ -1,0 +1,5 @@
+/* Forwarding header: the reference's include path for declarations that live in <gpusdrpipeline/abi/nodes.h>. */
+#ifndef GPUSDRPIPELINE_FWD_FILTERS_FILTER_H
+#define GPUSDRPIPELINE_FWD_FILTERS_FILTER_H
+#include <gpusdrpipeline/abi/nodes.h>
+#endif

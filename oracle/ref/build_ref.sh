@@ -99,5 +99,17 @@ if [ -f "$B200LIB/libb200sdr.so" ]; then
   link "$OUT/ref_tests_b200" "$B200LIB" b200sdr "${TESTS[@]}"
   link "$OUT/ref_chain_b200" "$B200LIB" b200sdr "$HERE/ref_chain.cpp"
 fi
+# ---- THIS repo's host framework (libgpusdrpipeline.so) behind the same sources --------------------------------
+#   *_ours     : compiled against the REFERENCE's headers, linked against our library  -> binary (vtable/ABI) compatibility
+#   *_ours_hdr : compiled against OUR re-authored headers                               -> source compatibility
+if [ -f "$B200LIB/libgpusdrpipeline.so" ]; then
+  OURS=(-L"$B200LIB" -lgpusdrpipeline -lb200sdr -L"$CUDA_HOME/lib64" -lcudart -lpthread -ldl '-Wl,-rpath,$ORIGIN/../../cuda_sdr_b200'
+        -Wl,-rpath,"$CUDA_HOME/lib64")
+  "$CXX" "${FLAGS[@]}" -o "$OUT/ref_tests_ours" "${TESTS[@]}" "${OURS[@]}"
+  "$CXX" "${FLAGS[@]}" -o "$OUT/ref_chain_ours" "$HERE/ref_chain.cpp" "${OURS[@]}"
+  HDR=(-std=c++20 -O2 -fPIC -w -DNDEBUG -I"$ROOT/include" -I"$HERE" -I"$CUDA_HOME/include")
+  "$CXX" "${HDR[@]}" -o "$OUT/ref_tests_ours_hdr" "${TESTS[@]}" "${OURS[@]}"
+  "$CXX" "${HDR[@]}" -DREF_CHAIN_HAS_FUSED -o "$OUT/ref_chain_ours_hdr" "$HERE/ref_chain.cpp" "${OURS[@]}"
+fi
 ls -la "$OUT"
 echo "build_ref: done"

@@ -15,8 +15,12 @@
 #include <cuComplex.h>
 #include <cuda_runtime.h>
 #include <gpusdrpipeline/Factories.h>
+#ifdef REF_CHAIN_HAS_FUSED
+#include <gpusdrpipeline/FusedChain.h>  // this repo's additive entry point: the whole chain as ONE Filter node
+#endif
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +58,7 @@ struct Args {
   double fs = 19.2e6, freq = 0, dev = 75e3;
   string mod = "am", taps1, taps2, in, out;
   size_t d1 = 1, d2 = 1, repeat = 1, step = 1 << 20;
+  bool fused = false;
 };
 
 static Args parse(int argc, char** argv) {
@@ -72,6 +77,7 @@ static Args parse(int argc, char** argv) {
     else if (k == "--out") a.out = v;
     else if (k == "--repeat") a.repeat = strtoull(v.c_str(), nullptr, 10);
     else if (k == "--step") a.step = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--fused") a.fused = v != "0";
     else {
       fprintf(stderr, "unknown argument %s\n", k.c_str());
       exit(2);
@@ -99,6 +105,75 @@ int main(int argc, char** argv) {
   ConstRef<ICudaCommandQueue> queue = unwrap(factories->getCudaCommandQueueFactory()->create(0));
   const float rfRate = static_cast<float>(a.fs);
   const float demodRate = static_cast<float>(a.fs / static_cast<double>(a.d1));
+
+  if (a.fused) {
+#ifdef REF_CHAIN_HAS_FUSED
+    // host int8 -> CudaMemcpy (pinned, H2D) -> ONE fused node -> CudaMemcpy (D2H) -> host float, same Filter contract
+    ConstRef<Filter> h2d = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyHostToDevice, queue));
+    ConstRef<Filter> d2h = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyDeviceToHost, queue));
+    GsFusedChainParams p {};
+    p.structSize = sizeof(p);
+    p.inputType = SampleType_Int8Complex;
+    p.modulation = fm ? Modulation_Fm : Modulation_Am;
+    p.mix = 1;
+    p.sampleRate = a.fs;
+    p.frequency = a.freq;
+    p.rfTaps = taps1.data();
+    p.rfTapCount = taps1.size();
+    p.rfDecimation = a.d1;
+    p.fmGain = demodRate / (2.0f * static_cast<float>(M_PI) * static_cast<float>(a.dev) * 5);
+    p.audioTaps = taps2.data();
+    p.audioTapCount = taps2.size();
+    p.audioDecimation = a.d2;
+    ConstRef<Filter> chain = unwrap(gsCreateFusedChain(&p, queue));
+    ConstRef<IAllocator> pinnedAlloc = unwrap(factories->getCudaAllocatorFactory()->createCudaAllocator(queue, 32, true));
+    ConstRef<IBufferFactory> pinnedFactory = unwrap(factories->createBufferFactory(pinnedAlloc));
+    ConstRef<IBuffer> host = unwrap(pinnedFactory->createBuffer(a.step * 4));
+    vector<float> result;
+    IBuffer* o[1];
+    size_t total = 0;
+    const auto start = chrono::steady_clock::now();
+    for (size_t rep = 0; rep < a.repeat; rep++) {
+      for (size_t pos = 0; pos < input.size();) {
+        const size_t step = input.size() - pos < a.step ? input.size() - pos : a.step;
+        Ref<IBuffer> staged = request(h2d, 0, step);
+        memcpy(staged->writePtr(), input.data() + pos, step);
+        THROW_IF_ERR(h2d->commitBuffer(0, step));
+        pos += step;
+        total += step / 2;
+        Ref<IBuffer> chainIn = request(chain, 0, h2d->getAlignedOutputDataSize(0));
+        o[0] = chainIn.get();
+        THROW_IF_ERR(h2d->readOutput(o, 1));
+        THROW_IF_ERR(chain->commitBuffer(0, chainIn->range()->used()));
+        Ref<IBuffer> d2hIn = request(d2h, 0, chain->getAlignedOutputDataSize(0));
+        o[0] = d2hIn.get();
+        THROW_IF_ERR(chain->readOutput(o, 1));
+        THROW_IF_ERR(d2h->commitBuffer(0, d2hIn->range()->used()));
+        while (d2h->getOutputDataSize(0) > 0) {
+          host->range()->clearRange();
+          o[0] = host.get();
+          THROW_IF_ERR(d2h->readOutput(o, 1));
+          cudaSetDevice(queue->cudaDevice());
+          cudaStreamSynchronize(queue->cudaStream());
+          const float* ptr = host->readPtr<float>();
+          result.insert(result.end(), ptr, ptr + host->range()->used() / sizeof(float));
+        }
+      }
+    }
+    const double secs = chrono::duration<double>(chrono::steady_clock::now() - start).count();
+    if (!a.out.empty()) {
+      FILE* f = fopen(a.out.c_str(), "wb");
+      if (!f || fwrite(result.data(), sizeof(float), result.size(), f) != result.size()) return 2;
+      fclose(f);
+    }
+    printf("{\"samples\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, \"repeat\": %zu, \"fused\": true}\n",
+           total, result.size(), secs, static_cast<double>(total) / secs / 1e6, a.step, a.repeat);
+    return 0;
+#else
+    fprintf(stderr, "--fused needs this repo's headers (REF_CHAIN_HAS_FUSED)\n");
+    return 2;
+#endif
+  }
 
   ConstRef<Filter> hostToDevice = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyHostToDevice, queue));
   ConstRef<Filter> int8ToFloat = unwrap(factories->getInt8ToFloatFactory()->createFilter(queue));

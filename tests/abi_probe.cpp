@@ -1,0 +1,80 @@
+// Compile-time and no-GPU run-time checks of the gpusdrpipeline boundary (built and run by tests/test_host_abi.py).
+// Layout facts are the ones measured on the reference's headers in SURVEY.md section 8(b).
+#include <gpusdrpipeline/Factories.h>
+#include <gpusdrpipeline/FusedChain.h>
+
+#include <cstddef>
+#include <cstdio>
+#include <type_traits>
+
+static_assert(sizeof(Status) == 4 && Status_ParseError == 9, "Status is uint32_t with ten codes in fixed order");
+static_assert(SampleType_FloatComplex == 0 && SampleType_Float == 1 && SampleType_Int8Complex == 2, "SampleType values");
+static_assert(Modulation_Am == 0 && Modulation_Fm == 1, "Modulation values");
+static_assert(sizeof(RefResult<IBuffer>) == 16 && offsetof(RefResult<IBuffer>, value) == 8, "RefResult layout");
+static_assert(sizeof(ValResult<size_t>) == 16 && offsetof(ValResult<size_t>, value) == 8, "ValResult<size_t> layout");
+static_assert(sizeof(ValResult<int32_t>) == 8 && offsetof(ValResult<int32_t>, value) == 4, "ValResult<int32_t> layout");
+static_assert(std::is_trivially_copyable<RefResult<IBuffer>>::value, "results are returned in registers");
+static_assert(std::is_same<Result<IBuffer>, RefResult<IBuffer>>::value && std::is_same<Result<int>, ValResult<int>>::value, "Result selection");
+static_assert(std::is_base_of<Sink, Filter>::value && std::is_base_of<Source, Filter>::value && std::is_base_of<Node, IDriver>::value, "hierarchy");
+static_assert(std::is_base_of<IDriver, IFilterDriver>::value && std::is_base_of<Filter, IFilterDriver>::value, "IFilterDriver is a driver and a Filter");
+
+int main() {
+  gslogSetVerbosity(GSLOG_FATAL);
+  Result<IFactories> r = getFactoriesSingleton();
+  if (r.status != Status_Success || r.value == nullptr) return 1;
+  IFactories* f = r.value;
+  const void* getters[] = {
+      f->getResizableBufferFactory(), f->getCudaAllocatorFactory(), f->getBufferSliceFactory(), f->getSysMemAllocator(), f->getSysMemCopier(),
+      f->getCudaBufferCopierFactory(), f->getBufferUtil(), f->getCudaMemcpyFilterFactory(), f->getAacFileWriterFactory(), f->getAddConstFactory(),
+      f->getAddConstToVectorLengthFactory(), f->getCosineSourceFactory(), f->getFileReaderFactory(), f->getFirFactory(),
+      f->getHackrfSourceFactory(), f->getInt8ToFloatFactory(), f->getMagnitudeFactory(), f->getMultiplyFactory(), f->getQuadDemodFactory(),
+      f->getSysMemSet(), f->getCudaMemSetFactory(), f->getSteppingDriverFactory(), f->getFilterDriverFactory(),
+      f->getPortRemappingSinkFactory(), f->getPortRemappingSourceFactory(), f->getRfToPcmAudioFactory(), f->getReadByteCountMonitorFactory(),
+      f->getDriverToDotFactory(), f->getBufferRangeFactory(), f->getCommandQueueFactory(), f->getCudaCommandQueueFactory()};
+  for (const void* g : getters)
+    if (g == nullptr) return 2;
+  if (getFactoriesSingleton().value != f) return 3;
+
+  // host-only pieces work without a GPU: system-memory buffers, ranges, slices, pools
+  ConstRef<IBufferFactory> buffers = unwrap(f->createSysMemBufferFactory());
+  ConstRef<IBuffer> buffer = unwrap(buffers->createBuffer(100));
+  if (buffer->range()->capacity() != 100 || buffer->range()->used() != 0) return 4;
+  if (buffer->range()->setUsedRange(10, 60) != Status_Success || buffer->range()->setUsedRange(70, 60) == Status_Success) return 5;
+  ConstRef<IBuffer> slice = unwrap(f->getBufferSliceFactory()->slice(buffer, 40, 80));
+  if (slice->range()->capacity() != 40 || slice->range()->offset() != 0 || slice->range()->endOffset() != 20) return 6;
+  if (slice->base() != buffer->base() + 40) return 7;
+  ConstRef<IBuffer> rest = unwrap(f->getBufferSliceFactory()->sliceRemaining(buffer));
+  if (rest->range()->capacity() != 40 || rest->range()->used() != 0 || rest->base() != buffer->base() + 60) return 8;
+  ConstRef<IBufferPool> pool = unwrap(f->createBufferPool(2, 64, buffers));
+  {
+    ConstRef<IBuffer> a = unwrap(pool->getBuffer());
+    ConstRef<IBuffer> b = unwrap(pool->getBuffer());
+    Result<IBuffer> none = pool->tryGetBuffer();
+    if (none.status != Status_Success || none.value != nullptr) return 9;
+  }
+  ConstRef<IBuffer> again = unwrap(pool->tryGetBuffer());
+  if (again == nullptr) return 10;
+  ConstRef<IRelocatableResizableBufferFactory> relocFactory = unwrap(f->createRelocatableSysMemBufferFactory());
+  ConstRef<IRelocatableResizableBuffer> reloc = unwrap(relocFactory->createRelocatableBuffer(64));
+  for (int i = 0; i < 64; i++) reloc->base()[i] = static_cast<uint8_t>(i);
+  if (reloc->range()->setUsedRange(40, 64) != Status_Success || reloc->relocateUsedToStart() != Status_Success) return 11;
+  if (reloc->range()->offset() != 0 || reloc->range()->used() != 24 || reloc->base()[0] != 40 || reloc->base()[23] != 63) return 12;
+  if (reloc->range()->setUsedRange(4, 64) != Status_Success || reloc->relocateUsedToStart() != Status_Success || reloc->base()[59] != 63 + 0) return 13;
+  if (reloc->resize(1000) != Status_Success || reloc->range()->capacity() < 1000 || reloc->base()[0] != 44) return 14;
+
+  // the registry knows the reference's node names; unknown names and bad JSON are errors, not crashes
+  if (!hasNodeFactory("Fir") || !hasNodeFactory("MultiplyCCC") || !hasNodeFactory("Component") || hasNodeFactory("nope")) return 15;
+  if (createNode("nope", "{}").status != Status_NotFound) return 16;
+  if (createNode("Fir", "{not json").status != Status_ParseError) return 17;
+  if (f->getHackrfSourceFactory()->createHackrfSource(0, 0, 1.0, 3).status != Status_NotFound) return 18;
+  if (f->getCommandQueueFactory()->exists("q0")) return 19;
+  if (f->getCommandQueueFactory()->getCudaCommandQueue("q0").status != Status_NotFound) return 20;
+
+  // no CPU fallback: with no CUDA device every GPU-facing creation fails with a Status, never with a crash
+  int deviceCount = 0;
+  if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0) {
+    if (f->getCudaCommandQueueFactory()->create(0).status == Status_Success) return 21;
+  }
+  std::printf("abi_probe ok (%d CUDA devices)\n", deviceCount);
+  return 0;
+}

@@ -30,7 +30,7 @@ def _need(name):
     return path
 
 
-@pytest.mark.parametrize("binary", ["ref_tests_b200", "ref_tests_naive", "ref_tests_ours"])
+@pytest.mark.parametrize("binary", ["ref_tests_b200", "ref_tests_naive", "ref_tests_ours", "ref_tests_ours_hdr"])
 def test_reference_gtests_pass_unmodified(binary):
     exe = _need(binary)
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
@@ -39,14 +39,14 @@ def test_reference_gtests_pass_unmodified(binary):
     assert "3 tests, 0 failed" in res.stdout, tail
 
 
-def _run_chain(exe, tmp_path, tag, x, t1, d1, t2, d2, mod, fs, freq, dev=75e3, step=1 << 20):
+def _run_chain(exe, tmp_path, tag, x, t1, d1, t2, d2, mod, fs, freq, dev=75e3, step=1 << 20, extra=()):
     x.tofile(tmp_path / "in.i8")
     t1.tofile(tmp_path / "t1.f32")
     t2.tofile(tmp_path / "t2.f32")
     out = tmp_path / f"out_{tag}.f32"
     cmd = [exe, "--fs", repr(fs), "--freq", repr(freq), "--mod", mod, "--dev", repr(dev), "--d1", str(d1), "--d2", str(d2),
            "--taps1", str(tmp_path / "t1.f32"), "--taps2", str(tmp_path / "t2.f32"), "--in", str(tmp_path / "in.i8"),
-           "--out", str(out), "--step", str(step)]
+           "--out", str(out), "--step", str(step), *extra]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
     info = json.loads(res.stdout.strip().splitlines()[-1])
@@ -64,10 +64,16 @@ def test_chain_through_reference_api(tmp_path, mod):
     t1 = taps.lowpass(101, 0.45 * fs / d1, fs)
     t2 = taps.lowpass(129, 0.45 * 48e3, fs / d1)
     results = {}
-    for tag in ("naive", "b200", "ours"):
+    for tag in ("naive", "b200", "ours", "ours_hdr"):
         exe = os.path.join(REF, f"ref_chain_{tag}")
         if os.path.exists(exe):
             results[tag] = _run_chain(exe, tmp_path, tag, x, t1, d1, t2, d2, mod, fs, freq)
+    exe = os.path.join(REF, "ref_chain_ours_hdr")
+    fused = None
+    if os.path.exists(exe):  # the same stream through ONE fused node of this repo's host library
+        fused = _run_chain(exe, tmp_path, "fused", x, t1, d1, t2, d2, mod, fs, freq, extra=("--fused", "1"))
+        fused_big = _run_chain(exe, tmp_path, "fused_big", x, t1, d1, t2, d2, mod, fs, freq, step=3 << 20, extra=("--fused", "1"))
+        assert np.array_equal(fused[0], fused_big[0]), "the fused node's output must not depend on the step size"
     if "naive" not in results or len(results) < 2:
         pytest.skip("oracle/_ref chain drivers not built")
     ref, info = results["naive"]
@@ -89,6 +95,12 @@ def test_chain_through_reference_api(tmp_path, mod):
     # (CosineSource.cpp:51,72,82), so only a loose bound holds here -- SURVEY.md section 0, fact 5
     spec = orc.ChainSpec(fs, freq, t1, d1, orc.AM if mod == "am" else orc.FM, gain, t2, d2)
     gold, _, _ = orc.chain(spec, x)
+    if fused is not None:  # exact mixer phase: the fused node meets the north-star tolerance against the fp64 oracle
+        assert fused[0].size == gold.size == ref.size
+        if mod == "fm":
+            assert_fm_close(fused[0], gold, gain, 2e-5, "fused node vs fp64 oracle")
+        else:
+            assert_close(fused[0], gold, REL_TOL, "fused node vs fp64 oracle")
     m = min(gold.size, ref.size)
     assert abs(gold.size - ref.size) <= 1
     if mod == "am":
