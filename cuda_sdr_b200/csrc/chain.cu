@@ -70,6 +70,8 @@ struct b200sdr_chain {
   float* dTapTable = nullptr;   // hT[D1][TS]
   float2* dMixTable = nullptr;  // W[D1]
   float2* dRotTable = nullptr;  // exp(j w m D1), m <= TS
+  unsigned* dBFrag = nullptr;   // tensor route: int8 digit fragments of the mixer-rotated tap matrix
+  float digitScale[3] = {0.0f, 0.0f, 0.0f};
   FirRoute tableRoute {};       // route the tables were laid out for (aligned input)
   ChainPlan fusedPlan {};       // fused persistent kernel (AM/FM with an audio FIR, aligned input), if the shape allows
   std::string variant;
@@ -119,6 +121,7 @@ B200SDR_EXPORT void b200sdr_chain_destroy(b200sdr_chain* c) {
   cudaFree(c->dTapTable);
   cudaFree(c->dMixTable);
   cudaFree(c->dRotTable);
+  cudaFree(c->dBFrag);
   delete c;
 }
 
@@ -196,6 +199,66 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
   char buf[256];
   if (c->hasAudioFir() && c->tableRoute.rows) {
     c->fusedPlan = planChain(c->elem, c->mix, nullptr, c->T1, c->D1, c->mod, c->T2, c->D2, c->device);
+  }
+  if (c->fusedPlan.fused && c->fusedPlan.conv) {
+    // B[k][n] of the tensor route (chain_kernels.cuh): k = 2p + (0: I, 1: Q), n = 2m + (0: re, 1: im),
+    // g[p][m] = h[m*D1 + p] * exp(j*w*p) / 128 evaluated in fp64, quantised to 24-bit fixed point = 3 signed int8 digits.
+    const unsigned D = c->D1, M = c->fusedPlan.M, KS = c->fusedPlan.kSteps, NT = (2u * c->fusedPlan.MP + 7u) / 8u;
+    const unsigned K = KS * 32u, N = NT * 8u;
+    std::vector<double> B(static_cast<size_t>(K) * N, 0.0);
+    double bMax = 0.0;
+    for (unsigned p = 0; p < D; p++) {
+      double wr = static_cast<double>(c->inScale), wi = 0.0;
+      if (c->mix) {
+        const double frac = static_cast<double>(static_cast<int64_t>(c->phaseStep * p)) * (1.0 / 18446744073709551616.0);
+        const double phi = 6.283185307179586476925286766559 * frac;
+        wr = std::cos(phi) * c->inScale;
+        wi = std::sin(phi) * c->inScale;
+      }
+      for (unsigned m = 0; m < M; m++) {
+        const size_t j = static_cast<size_t>(m) * D + p;
+        const double h = j < c->T1 ? static_cast<double>(cfg->rf_taps[j]) : 0.0;
+        const double gr = h * wr, gi = h * wi;
+        B[static_cast<size_t>(2 * p) * N + 2 * m] = gr;
+        B[static_cast<size_t>(2 * p + 1) * N + 2 * m] = -gi;
+        B[static_cast<size_t>(2 * p) * N + 2 * m + 1] = gi;
+        B[static_cast<size_t>(2 * p + 1) * N + 2 * m + 1] = gr;
+      }
+    }
+    for (double v : B) bMax = std::fmax(bMax, std::fabs(v));
+    // three balanced digits in [-128, 127] reach 127*65536 + 127*256 + 127 = 8 355 711 on the positive side
+    const double scale = bMax > 0.0 ? 8355711.0 / bMax : 1.0;
+    c->digitScale[0] = static_cast<float>(1.0 / scale);
+    c->digitScale[1] = static_cast<float>(256.0 / scale);
+    c->digitScale[2] = static_cast<float>(65536.0 / scale);
+    std::vector<unsigned> frag(c->fusedPlan.bFragWords, 0u);
+    auto digits = [&](double v, int out[3]) {  // q = d2*65536 + d1*256 + d0 with every digit in [-128, 127]
+      long long q = std::llround(v * scale);
+      for (int d = 0; d < 3; d++) {
+        long long r = ((q % 256) + 256) % 256;
+        if (r >= 128) r -= 256;
+        out[d] = static_cast<int>(r);
+        q = (q - r) / 256;
+      }
+    };
+    for (unsigned n8 = 0; n8 < NT; n8++)
+      for (unsigned ks = 0; ks < KS; ks++)
+        for (unsigned half = 0; half < 2; half++)
+          for (unsigned lane = 0; lane < 32; lane++) {
+            const unsigned g = lane >> 2, t = lane & 3u;
+            unsigned word[3] = {0, 0, 0};
+            for (unsigned e = 0; e < 4; e++) {
+              const unsigned k = ks * 32u + half * 16u + t * 4u + e, n = n8 * 8u + g;
+              int dg[3];
+              digits(B[static_cast<size_t>(k) * N + n], dg);
+              for (int d = 0; d < 3; d++) word[d] |= (static_cast<unsigned>(dg[d]) & 0xffu) << (8u * e);
+            }
+            for (unsigned d = 0; d < 3; d++) frag[(((d * NT + n8) * KS + ks) * 2u + half) * 32u + lane] = word[d];
+          }
+    if (!upload(frag.data(), frag.size() * sizeof(unsigned), reinterpret_cast<void**>(&c->dBFrag))) {
+      b200sdr_chain_destroy(c);
+      return st;
+    }
   }
   if (c->fusedPlan.fused) {
     c->variant = chainVariantName(c->elem, c->mix, c->fusedPlan, buf, sizeof(buf));
@@ -315,6 +378,11 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
     prm.mixTable = c->dMixTable;
     prm.rotTable = c->dRotTable;
     prm.taps2 = c->dTaps2;
+    prm.bFrag = c->dBFrag;
+    prm.kSteps = c->fusedPlan.kSteps;
+    prm.digitScale[0] = c->digitScale[0];
+    prm.digitScale[1] = c->digitScale[1];
+    prm.digitScale[2] = c->digitScale[2];
     prm.nIn = numInputs;
     prm.nAudio = numAudio;
     prm.T1 = c->T1;

@@ -1,11 +1,13 @@
 // Instantiations of chainKernel for ELEM=kElemComplex, MIX=false (see chain_launch.cu: chainKernelFor).
+// Per MP: rows per lane {1, 2, 4 (2 when MP > 4)} x route {CUDA cores, int8 tensor cores (int8 input only)}.
 #include "chain_dispatch.h"
 #include "chain_kernels.cuh"
 
 namespace b200sdr {
-#define CHAIN_SET(MP)                                                                                       \
-  chainKernel<kElemComplex, false, MP, 2, 0>, chainKernel<kElemComplex, false, MP, 2, 0>,                                    \
+#define CHAIN_SET(MP)                                                                       \
+  chainKernel<kElemComplex, false, MP, 1, 0>, chainKernel<kElemComplex, false, MP, 1, 0>,               \
+      chainKernel<kElemComplex, false, MP, 2, 0>, chainKernel<kElemComplex, false, MP, 2, 0>,           \
       chainKernel<kElemComplex, false, MP, (MP <= 4 ? 4 : 2), 0>, chainKernel<kElemComplex, false, MP, (MP <= 4 ? 4 : 2), 0>
-const ChainKernel kChainCf32Plain[32] = {CHAIN_SET(1), CHAIN_SET(2), CHAIN_SET(3), CHAIN_SET(4),
+const ChainKernel kChainCf32Plain[48] = {CHAIN_SET(1), CHAIN_SET(2), CHAIN_SET(3), CHAIN_SET(4),
                                 CHAIN_SET(5), CHAIN_SET(6), CHAIN_SET(7), CHAIN_SET(8)};
 }  // namespace b200sdr

@@ -12,9 +12,12 @@ struct ChainParams;
 struct ChainPlan {
   bool fused;  // false: this shape/alignment has to take the two-kernel path (rowsKernel/directKernel + audio FIR)
   unsigned M, MP, TS;
-  unsigned rpt, rptIdx, conv;
-  unsigned rowsPerTile, outPerTile;
-  unsigned stages, audioParts, dmCapacity;
+  unsigned rpt, rptIdx;
+  unsigned conv;                    // 0: CUDA cores (packed FP32, ALU-pipe int8 conversion); 1: int8 tensor cores (int8 input only)
+  unsigned kSteps, bFragWords;      // tensor route: ceil(2*D1/32) k-steps; words of the B-fragment table
+  unsigned computeWarps, audioWarps;  // per CTA; blockDim = 32 * (computeWarps + audioWarps)
+  unsigned tileRows, outPerTile;    // rows staged per tile, demodulated samples it yields
+  unsigned stages, dmCapacity;
   unsigned smemBytes, ctasPerSm, grid;
 };
 
@@ -24,7 +27,7 @@ cudaError_t launchChain(int elem, bool mix, const ChainPlan& plan, ChainParams p
 const char* chainVariantName(int elem, bool mix, const ChainPlan& plan, char* buf, size_t bufLen);
 
 using ChainKernel = void (*)(const ChainParams);
-// [MP-1][rptIdx (0: 2 rows/thread, 1: 4 rows/thread; MP > 4 always 2)][conv (0: magic-number/FADD2, 1: sign-extend/I2FP)]
-extern const ChainKernel kChainInt8Mix[32], kChainInt8Plain[32], kChainCf32Mix[32], kChainCf32Plain[32];
+// [MP-1][rptIdx (0: 1 row/lane, 1: 2 rows/lane, 2: 4 rows/lane; MP > 4: 2)][conv (0: CUDA cores, 1: tensor cores)]
+extern const ChainKernel kChainInt8Mix[48], kChainInt8Plain[48], kChainCf32Mix[48], kChainCf32Plain[48];
 
 }  // namespace b200sdr

@@ -89,6 +89,9 @@ __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t arrivals) {
 __device__ __forceinline__ void fenceMbarInit() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }

@@ -164,8 +164,11 @@ def test_two_kernel_path_segments_concatenate_bit_exactly(sdr, monkeypatch):
     {"B200SDR_FUSED": "0"}, {"B200SDR_FUSED": "1"},
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "2"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "4"},
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "1"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "2", "B200SDR_CHAIN_CTAS": "1"},
-    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_CONV": "0"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_CONV": "1"},
-    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_PARTS": "1"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_PARTS": "8"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_MMA": "0"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_MMA": "1"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_WARPS": "2"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_WARPS": "8"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "1", "B200SDR_CHAIN_WARPS": "12"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_AUDIO_WARPS": "3"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_MMA": "0", "B200SDR_CHAIN_RPT": "1"},
+    {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "3", "B200SDR_CHAIN_RPT": "2"},
 ])
 @pytest.mark.parametrize("which", ["c2", "c3"])
 def test_every_kernel_variant_matches_the_oracle(sdr, monkeypatch, env, which):
@@ -177,6 +180,11 @@ def test_every_kernel_variant_matches_the_oracle(sdr, monkeypatch, env, which):
     x = sdr.synth.int8_iq(400000 + 17, seed=11)
     chain, _ = check_chain(sdr, kw, x, n0=4242, what=f"{which} {env}")
     assert chain.fused == (env.get("B200SDR_FUSED") == "1")
+
+
+def test_default_route_is_fused_for_c2_and_two_kernels_for_c3(sdr):
+    assert sdr.Chain(**c2_spec(sdr)).variant.startswith("chain<int8c,mix=1,MP=3,RPT=2,conv=imma>")
+    assert sdr.Chain(**c3_spec(sdr)).variant.startswith("rows<int8c,mix=1,MP=7")
 
 
 def test_host_path_equals_device_path(sdr):

@@ -9,15 +9,13 @@ run() {
     python -c "import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({'env': '$*', 'kernel_ms': d['roofline']['kernel_ms'], 'frac': d['roofline']['frac'], 'variant': d['config']['kernel_variant']}))" >> $OUT
 }
 run B200SDR_FUSED=0
-for conv in 1 0; do
-  for rpt in 4 2; do
+for rpt in 4 2; do
+  for warps in 4 8; do
     for stages in 1 2 3; do
-      for ctas in 0; do
-        run B200SDR_FUSED=1 B200SDR_CHAIN_CONV=$conv B200SDR_CHAIN_RPT=$rpt B200SDR_CHAIN_STAGES=$stages
-      done
+      run B200SDR_FUSED=1 B200SDR_CHAIN_RPT=$rpt B200SDR_CHAIN_WARPS=$warps B200SDR_CHAIN_STAGES=$stages
     done
   done
 done
-run B200SDR_FUSED=1 B200SDR_CHAIN_PARTS=1
-run B200SDR_FUSED=1 B200SDR_CHAIN_PARTS=4
+run B200SDR_FUSED=1 B200SDR_CHAIN_MMA=0
+run B200SDR_FUSED=1 B200SDR_CHAIN_CTAS=1
 cat $OUT
