@@ -74,7 +74,8 @@ def config_dict(args, wl, extra=None):
         "modulation": "am" if wl["mod"] == 0 else "fm",
         "phase_mode": "exact (64-bit fixed-point turns)",
         "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
-        "parallelism": "overlapped time segments, one per GPU; NCCL send/recv gather of audio to rank 0",
+        "parallelism": "overlapped time segments, one per GPU; NCCL send/recv gather of the audio to rank 0 on a side stream, "
+                       "overlapping the next step's kernel",
     }
     if extra:
         cfg.update(extra)
@@ -159,6 +160,46 @@ def cpu_chain_rate(wl, target_seconds: float, max_log2: int = 26):
     return n / dt / 1e6, orc.num_threads(), f"2^{log2} samples of the same workload, one pass, fp64 oracle (oracle/oracle.c), OpenMP", n, dt
 
 
+def reference_api_rates(wl, log2_samples: int = 24):
+    """Throughput of the chain driven through the REFERENCE'S Filter API in <= 1 MiB steps, host buffers in and out
+    (oracle/ref/ref_chain.cpp, built by oracle/ref/build_ref.sh into oracle/_ref/):
+      reference_cuda_pipeline : the reference's own host framework (compiled in place) + a plain restated gsdr  (= B1)
+      ours_filter_api_fused   : this repo's libgpusdrpipeline.so, the same Filter contract, ONE fused node, 64 MiB steps
+    Returns {} when the binaries are not there (they need /root/reference at build time)."""
+    import numpy as np
+
+    out = {}
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    naive, ours = os.path.join(ref_dir, "ref_chain_naive"), os.path.join(ref_dir, "ref_chain_ours_hdr")
+    if not os.path.exists(naive) and not os.path.exists(ours):
+        return out
+    n = 1 << log2_samples
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        rng = np.random.default_rng(0x5D120001)
+        rng.integers(-100, 101, size=2 * n, dtype=np.int8).tofile(os.path.join(tmp, "in.i8"))
+        np.asarray(wl["t1"], dtype=np.float32).tofile(os.path.join(tmp, "t1.f32"))
+        np.asarray(wl["t2"], dtype=np.float32).tofile(os.path.join(tmp, "t2.f32"))
+        base = ["--fs", repr(wl["fs"]), "--freq", repr(wl["f"]), "--mod", "am" if wl["mod"] == 0 else "fm", "--d1", str(wl["d1"]),
+                "--d2", str(wl["d2"]), "--taps1", os.path.join(tmp, "t1.f32"), "--taps2", os.path.join(tmp, "t2.f32"),
+                "--in", os.path.join(tmp, "in.i8")]
+        runs = [("reference_cuda_pipeline", naive, ["--repeat", "4"],
+                 "reference host framework compiled in place + restated one-thread-per-output gsdr kernels (B1), <= 1 MiB steps, "
+                 "pinned host in / host out"),
+                ("ours_filter_api_fused", ours, ["--repeat", "16", "--fused", "1", "--step", str(64 << 20)],
+                 "this repo's libgpusdrpipeline.so through the same Filter contract: CudaMemcpy -> ONE fused node -> CudaMemcpy, "
+                 "64 MiB steps")]
+        for key, exe, extra, what in runs:
+            if not os.path.exists(exe):
+                continue
+            try:
+                res = subprocess.run([exe] + base + extra, capture_output=True, text=True, timeout=300)
+                info = json.loads(res.stdout.strip().splitlines()[-1])
+                out[key] = {"value": info["msps"], "unit": UNIT, "samples": info["samples"], "what": what}
+            except Exception as e:  # a baseline, never fatal for the bench line
+                out[key] = {"value": None, "error": str(e)[:200]}
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -220,7 +261,20 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator comes up; stdout must carry ONE JSON line, so fd 1
+        # points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            probe = torch.zeros(1, device=dev)
+            dist.all_reduce(probe)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     wl = workload(args.workload)
     n = 1 << args.log2_block
@@ -229,46 +283,72 @@ def run_ours(args):
     n_rf, n_demod, n_audio = chain.counts(n)
     x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120001 + rank)  # this rank's time segment of the stream
     demod = torch.empty(n_demod, dtype=torch.float32, device=dev)
-    audio = torch.empty(n_audio, dtype=torch.float32, device=dev)
+    # Audio of GATHER_EVERY consecutive steps is collected in one of two slabs; a full slab is gathered to rank 0 with ONE
+    # batched send/recv on a side stream while the next slab fills (the exchange is ~1 % of the input bytes: what it costs
+    # is host-side enqueue time per call, hence the batching)
+    GATHER_EVERY = 8
+    slabs = [torch.empty(GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
     first_index = rank * n  # absolute sample index of the segment (mixer phase)
-    counts = [n_audio] * world
-    gathered = torch.empty(n_audio * world, dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    gathered = [torch.empty(world, GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    slab_full = [torch.cuda.Event() for _ in range(2)]
+    slab_drained = [torch.cuda.Event() for _ in range(2)]
+    step_no = [0]
 
-    def gather():
+    def gather(slab, count):
+        """Decimated audio of every rank -> rank 0 (the only exchange on the path), on the side stream."""
         if world == 1:
             return
-        if rank == 0:
-            gathered[:n_audio] = audio
-            reqs = [dist.irecv(gathered[r * n_audio:(r + 1) * n_audio], src=r) for r in range(1, world)]
-            for r in reqs:
-                r.wait()
-        else:
-            dist.send(audio, dst=0)
+        slab_full[slab].record()
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(slab_full[slab])
+            if rank == 0:
+                gathered[slab][0, :count].copy_(slabs[slab][:count], non_blocking=True)
+                ops = [dist.P2POp(dist.irecv, gathered[slab][r, :count], r) for r in range(1, world)]
+            else:
+                ops = [dist.P2POp(dist.isend, slabs[slab][:count], 0)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            slab_drained[slab].record()
 
     k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     fused = chain.variant.startswith("chain<")
 
-    def step(i=None):
+    def step(i=None, last=False):
+        k = step_no[0]
+        step_no[0] += 1
+        slab, slot = (k // GATHER_EVERY) & 1, k % GATHER_EVERY
+        if world > 1 and slot == 0:
+            torch.cuda.current_stream().wait_event(slab_drained[slab])  # this slab's previous gather has drained
         if i is not None:
             k1_events[i][0].record()
-        got = chain.process_device(x, first_index, out=audio, scratch=demod)  # fused: ONE kernel; else K1 + K2
+        got = chain.process_device(x, first_index, out=slabs[slab][slot], scratch=demod)  # fused: ONE kernel; else K1 + K2
         if i is not None:
             k1_events[i][1].record()
         assert got.numel() == n_audio
-        gather()
+        if slot == GATHER_EVERY - 1 or last:
+            gather(slab, slot + 1)
+            step_no[0] += GATHER_EVERY - 1 - slot  # a partial slab at the end of a phase: start the next phase on a fresh slab
 
     def barrier():
         if world > 1:
+            torch.cuda.current_stream().wait_stream(comm_stream)
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm-up: first the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would
+    # run different counts), then max(W, 3) complete steps including the gather, in lockstep on every rank
     warm_steps = 0
     t_warm = time.perf_counter()
-    while warm_steps < max(args.warmup, 3) or time.perf_counter() - t_warm < args.warmup_seconds:
-        step()
+    while time.perf_counter() - t_warm < args.warmup_seconds:
+        chain.process_device(x, first_index, out=slabs[0][0], scratch=demod)
         warm_steps += 1
         if warm_steps % 16 == 0:
             torch.cuda.synchronize()
+    n_warm = max(args.warmup, 3)
+    for w in range(n_warm):
+        step(last=(w == n_warm - 1))
+        warm_steps += 1
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -278,7 +358,9 @@ def run_ours(args):
     barrier()
     t_start.record()
     for i in range(args.steps):
-        step(i)
+        step(i, last=(i == args.steps - 1))
+    if world > 1:
+        torch.cuda.current_stream().wait_stream(comm_stream)  # the last gathers are part of the timed region
     t_end.record()
     barrier()
     launches = sdr._native.launch_count() - launches0
@@ -326,21 +408,30 @@ def run_ours(args):
             alg_bytes = 2.0 * n + 8.0 * n_demod + 4.0 * n_audio
             kernel_name = "rowsKernel + directKernel (two launches per step)"
         achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel variant (profiles/)
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if chain.variant.startswith(t["variant_prefix"]) and t["samples_per_launch"] == n:
+                traffic = t["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": warm_steps, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, wl, {"kernel_variant": chain.variant}),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": kernel_name, "kernel_ms": k1_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
             v, cores, sample, _, _ = cpu_chain_rate(wl, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and not args.skip_e2e:
+            line.update(reference_api_rates(wl))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

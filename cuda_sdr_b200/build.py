@@ -27,7 +27,7 @@ NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nv
 CXX = "/usr/bin/g++"  # the image's $CXX is a trimmed wrapper; use the system compiler
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-ccbin", CXX,
-                     "-I" + INCLUDE, "-I" + CSRC]
+                     "-I" + INCLUDE, "-I" + CSRC] + os.environ.get("NVCC_EXTRA", "").split()
 
 
 def _newer(target: str, sources: list[str]) -> bool:

@@ -6,6 +6,13 @@
 
 #include "fir_kernels.cuh"
 
+// cycle counters inside the kernel cost issue slots; they are compiled in only for tools (-DB200SDR_CHAIN_PROFILE_BUILD)
+#ifdef B200SDR_CHAIN_PROFILE_BUILD
+#define B200SDR_PROF(prm__) ((prm__).prof != nullptr)
+#else
+#define B200SDR_PROF(prm__) false
+#endif
+
 namespace b200sdr {
 
 struct ChainParams {
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
   const unsigned tileBytes = lay.tileBytes, slotStride = lay.slotStride;
 
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
-  const long long tEntry = prm.prof ? clock64() : 0;
+  const long long tEntry = B200SDR_PROF(prm) ? clock64() : 0;
 
   // ---- this CTA's run of audio outputs ---------------------------------------------------------------
   const unsigned long long per = prm.nAudio / gridDim.x, extra = prm.nAudio % gridDim.x;
@@ -403,12 +410,12 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
     if constexpr (MIX) rot1 = rot[1];
 
     long long cWait = 0, cMain = 0, cRest = 0, cLine = 0;
-    const long long tLoop = prm.prof ? clock64() : 0;
+    const long long tLoop = B200SDR_PROF(prm) ? clock64() : 0;
     unsigned slot = 0, slotPhase = 0;  // t % S and (t / S) & 1 without the divisions
     for (unsigned t = 0; t < nTiles; t++) {
-      const long long t0 = prm.prof ? clock64() : 0;
+      const long long t0 = B200SDR_PROF(prm) ? clock64() : 0;
       mbarWait(&full[slot], slotPhase);
-      const long long t1 = prm.prof ? clock64() : 0;
+      const long long t1 = B200SDR_PROF(prm) ? clock64() : 0;
 
       float2 acc[RPT][MP];
       const unsigned char* block = tiles + slot * slotStride + warp * OTW * D * ES;
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
       } else {
         tilePartialSums<ELEM, MIX, MP, RPT, CONV>(block, hT, W, D, lane, 32u, acc);
       }
-      const long long t2 = prm.prof ? clock64() : 0;
+      const long long t2 = B200SDR_PROF(prm) ? clock64() : 0;
       // ---- the slot is free once every compute warp is past its main loop; the last one refills it ----------------
       __syncwarp();
       if (t + S < nTiles) {
@@ -484,9 +491,9 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
 
       // ---- demodulate into the line (after the audio warp has handed it back) -----------------------------------
       const unsigned cur = t & 1u, use = t >> 1;
-      const long long t3 = prm.prof ? clock64() : 0;
+      const long long t3 = B200SDR_PROF(prm) ? clock64() : 0;
       if (use > 0) mbarWait(&dmEmpty[cur], (use - 1) & 1u);
-      const long long t4 = prm.prof ? clock64() : 0;
+      const long long t4 = B200SDR_PROF(prm) ? clock64() : 0;
       float* line = dm + cur * prm.dmCapacity + carry + warp * OTW;
       if (fm) {
 #pragma unroll
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
         slot = 0;
         slotPhase ^= 1u;
       }
-      if (prm.prof) {
+      if (B200SDR_PROF(prm)) {
         const long long t5 = clock64();
         cWait += t1 - t0;
         cMain += t2 - t1;
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
         cRest += (t3 - t2) + (t5 - t4);
       }
     }
-    if (prm.prof && lane == 0) {
+    if (B200SDR_PROF(prm) && lane == 0) {
       unsigned long long* o = prm.prof + (static_cast<unsigned long long>(blockIdx.x) * NW + warp) * 6;
       o[0] = cWait;
       o[1] = cMain;

@@ -135,7 +135,11 @@ cudaError_t launchChain(int elem, bool mix, const ChainPlan& plan, ChainParams p
   unsigned grid = plan.grid;
   if (static_cast<unsigned long long>(grid) > prm.nAudio) grid = static_cast<unsigned>(prm.nAudio);
   // tools only: B200SDR_CHAIN_PROFILE=1 prints where the compute warps spend their cycles (synchronises!)
+#ifdef B200SDR_CHAIN_PROFILE_BUILD
   static const bool profile = envInt("B200SDR_CHAIN_PROFILE", 0) != 0;
+#else
+  constexpr bool profile = false;  // build with NVCC_EXTRA=-DB200SDR_CHAIN_PROFILE_BUILD to enable (tools/chain_profile.sh)
+#endif
   unsigned long long* prof = nullptr;
   if (profile) {
     cudaMalloc(&prof, sizeof(unsigned long long) * 6 * grid * plan.computeWarps);
