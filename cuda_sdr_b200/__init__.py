@@ -6,6 +6,7 @@ framework mirroring the reference's getFactoriesSingleton()/Filter interface).
 """
 from . import _native  # noqa: F401  (loads libb200sdr.so or raises)
 from .chain import AM, FM, NONE, Chain, fm_gain  # noqa: F401
+from .channelizer import Channelizer  # noqa: F401
 from . import ops, sharding, synth, taps  # noqa: F401
 
-__all__ = ["AM", "FM", "NONE", "Chain", "fm_gain", "ops", "taps", "synth", "sharding"]
+__all__ = ["AM", "FM", "NONE", "Chain", "Channelizer", "fm_gain", "ops", "taps", "synth", "sharding"]

@@ -54,6 +54,18 @@ class ChainConfig(C.Structure):
     ]
 
 
+class ChannelizerConfig(C.Structure):
+    """Mirror of b200sdr_channelizer_config (include/b200sdr/b200sdr.h)."""
+
+    _fields_ = [
+        ("struct_size", u32), ("num_channels", u32), ("sample_rate", f64),
+        ("frequencies", C.POINTER(f64)), ("modulations", C.POINTER(u32)), ("fm_gains", C.POINTER(f32)),
+        ("rf_taps", C.POINTER(f32)), ("rf_tap_count", sz), ("rf_decimation", sz),
+        ("audio_taps", C.POINTER(f32)), ("audio_tap_count", sz), ("audio_decimation", sz),
+        ("cuda_device", i32), ("reserved", u32),
+    ]
+
+
 psz = C.POINTER(sz)
 B200SDR_SYMBOLS = {
     "b200sdr_chain_create": (u32, [C.POINTER(ChainConfig), C.POINTER(vp)]),
@@ -71,6 +83,11 @@ B200SDR_SYMBOLS = {
     "b200sdr_chain_process_device": (u32, [vp, vp, sz, u64, vp, vp, sz, psz, stream_t]),
     "b200sdr_chain_process_host": (u32, [vp, vp, sz, u64, vp, sz, psz]),
     "b200sdr_chain_set_host_segment": (u32, [vp, sz]),
+    "b200sdr_channelizer_create": (u32, [vp, C.POINTER(vp)]),
+    "b200sdr_channelizer_destroy": (None, [vp]),
+    "b200sdr_channelizer_counts": (None, [vp, sz, psz, psz]),
+    "b200sdr_channelizer_run": (u32, [vp, vp, sz, vp, sz, vp, sz, sz, stream_t]),
+    "b200sdr_channelizer_variant": (C.c_char_p, [vp]),
     "b200sdr_launch_count": (u64, []),
     "b200sdr_chain_variant": (C.c_char_p, [vp]),
     "b200sdr_version": (C.c_char_p, []),

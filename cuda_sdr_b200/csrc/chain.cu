@@ -32,6 +32,14 @@ b200sdr_status cudaFail(cudaError_t e, const char* where) {
   return e == cudaErrorMemoryAllocation ? B200SDR_OUT_OF_MEMORY : B200SDR_RUNTIME_ERROR;
 }
 
+}  // namespace
+
+namespace b200sdr {
+b200sdr_status chainFail(b200sdr_status status, const std::string& what) { return fail(status, what); }
+}  // namespace b200sdr
+
+namespace {
+
 #define CUDA_OR_RETURN(call)                              \
   do {                                                    \
     const cudaError_t e__ = (call);                       \

@@ -1,0 +1,269 @@
+// The wideband channelizer behind include/b200sdr/b200sdr.h: table construction (fp64 -> 24-bit fixed point ->
+// IMMA fragment order), the RF kernel launch over (channel groups x row tiles) and the batched audio FIR.
+#include <b200sdr/b200sdr.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "channel_kernels.cuh"
+#include "fir_dispatch.h"
+#include "fir_kernels.cuh"
+
+using namespace b200sdr;
+
+namespace b200sdr {
+b200sdr_status chainFail(b200sdr_status status, const std::string& what);  // chain.cu: sets b200sdr_last_error()
+}
+
+namespace {
+
+size_t firCount(size_t nIn, size_t T, size_t D) { return (T == 0 || nIn + 1 < T) ? 0 : (nIn + 1 - T) / (D == 0 ? 1 : D); }
+
+b200sdr_status cudaFailC(cudaError_t e, const char* where) {
+  return chainFail(e == cudaErrorMemoryAllocation ? B200SDR_OUT_OF_MEMORY : B200SDR_RUNTIME_ERROR, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+}  // namespace
+
+struct b200sdr_channelizer {
+  int device = 0;
+  unsigned C = 0, T1 = 0, D1 = 1, M = 0, NTC = 1, KS = 0, T2 = 0, D2 = 1, groups = 0, warps = 4;
+  bool anyFm = false;
+  unsigned* dBFrag = nullptr;
+  float2* dRot = nullptr;
+  float* dScale = nullptr;
+  float* dGain = nullptr;
+  int* dMod = nullptr;
+  float* dTaps2 = nullptr;
+  std::string variant;
+};
+
+B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
+  if (!c) return;
+  DeviceGuard guard(c->device);
+  cudaFree(c->dBFrag);
+  cudaFree(c->dRot);
+  cudaFree(c->dScale);
+  cudaFree(c->dGain);
+  cudaFree(c->dMod);
+  cudaFree(c->dTaps2);
+  delete c;
+}
+
+B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer* c) { return c ? c->variant.c_str() : ""; }
+
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channelizer_config* cfg, b200sdr_channelizer** out) {
+  if (!cfg || !out) return chainFail(B200SDR_INVALID_ARGUMENT, "config and out must be non-null");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(b200sdr_channelizer_config)) return chainFail(B200SDR_INVALID_ARGUMENT, "struct_size mismatch");
+  if (cfg->num_channels == 0 || !cfg->frequencies || !cfg->modulations) return chainFail(B200SDR_INVALID_ARGUMENT, "channels are required");
+  if (!cfg->rf_taps || cfg->rf_tap_count == 0 || !cfg->audio_taps || cfg->audio_tap_count == 0)
+    return chainFail(B200SDR_INVALID_ARGUMENT, "RF and audio taps are required");
+  if (!(cfg->sample_rate > 0.0)) return chainFail(B200SDR_INVALID_ARGUMENT, "sample_rate must be positive");
+  const size_t D = cfg->rf_decimation == 0 ? 1 : cfg->rf_decimation;
+  const size_t M = (cfg->rf_tap_count + D - 1) / D;
+  if (D % 8 != 0 || D > (1u << 20)) return chainFail(B200SDR_INVALID_ARGUMENT, "rf_decimation must be a multiple of 8");
+  if (M > 8) return chainFail(B200SDR_INVALID_ARGUMENT, "at most 8 taps per decimation phase (rf_tap_count <= 8 * rf_decimation)");
+  for (uint32_t i = 0; i < cfg->num_channels; i++) {
+    if (cfg->modulations[i] > B200SDR_MOD_FM) return chainFail(B200SDR_INVALID_ARGUMENT, "channel modulation must be AM or FM");
+    if (cfg->modulations[i] == B200SDR_MOD_FM && !cfg->fm_gains) return chainFail(B200SDR_INVALID_ARGUMENT, "fm_gains is required for FM channels");
+  }
+
+  b200sdr_channelizer* c = new (std::nothrow) b200sdr_channelizer();
+  if (!c) return chainFail(B200SDR_OUT_OF_MEMORY, "host allocation failed");
+  c->device = cfg->cuda_device;
+  c->C = cfg->num_channels;
+  c->T1 = static_cast<unsigned>(cfg->rf_tap_count);
+  c->D1 = static_cast<unsigned>(D);
+  c->M = static_cast<unsigned>(M);
+  c->NTC = M <= 4 ? 1u : 2u;
+  c->KS = (2u * c->D1 + 31u) / 32u;
+  c->T2 = static_cast<unsigned>(cfg->audio_tap_count);
+  c->D2 = cfg->audio_decimation == 0 ? 1u : static_cast<unsigned>(cfg->audio_decimation);
+  c->groups = (c->C + kChanNC - 1) / kChanNC;
+  const char* w = std::getenv("B200SDR_CHANNEL_WARPS");
+  c->warps = (w && std::atoi(w) == 8) ? 8u : 4u;
+
+  // ---- tables -----------------------------------------------------------------------------------------------
+  const unsigned K = c->KS * 32u, NCOL = c->NTC * 8u, NT = kChanNC * c->NTC;
+  const size_t chunkWords = static_cast<size_t>(NT) * 3u * 64u;
+  std::vector<unsigned> frag(static_cast<size_t>(c->groups) * c->KS * chunkWords, 0u);
+  std::vector<float2> rot(static_cast<size_t>(c->C) * 8u, make_float2(1.0f, 0.0f));
+  std::vector<float> scales(static_cast<size_t>(c->C) * 3u, 0.0f), gains(c->C, 1.0f);
+  std::vector<int> mods(c->C, 0);
+  std::vector<double> B(static_cast<size_t>(K) * NCOL);
+  const double twoPi = 6.283185307179586476925286766559;
+  for (unsigned ch = 0; ch < c->C; ch++) {
+    const uint64_t step = phaseStepOf(cfg->frequencies[ch], cfg->sample_rate);
+    auto phasor = [&](uint64_t turns, double& re, double& im) {
+      const double phi = twoPi * (static_cast<double>(static_cast<int64_t>(turns)) * (1.0 / 18446744073709551616.0));
+      re = std::cos(phi);
+      im = std::sin(phi);
+    };
+    std::fill(B.begin(), B.end(), 0.0);
+    double bMax = 0.0;
+    for (unsigned p = 0; p < c->D1; p++) {
+      double wr, wi;
+      phasor(step * p, wr, wi);
+      wr *= 1.0 / 128.0;
+      wi *= 1.0 / 128.0;
+      for (unsigned m = 0; m < c->M; m++) {
+        const size_t j = static_cast<size_t>(m) * c->D1 + p;
+        const double h = j < c->T1 ? static_cast<double>(cfg->rf_taps[j]) : 0.0;
+        const double gr = h * wr, gi = h * wi;
+        B[static_cast<size_t>(2 * p) * NCOL + 2 * m] = gr;
+        B[static_cast<size_t>(2 * p + 1) * NCOL + 2 * m] = -gi;
+        B[static_cast<size_t>(2 * p) * NCOL + 2 * m + 1] = gi;
+        B[static_cast<size_t>(2 * p + 1) * NCOL + 2 * m + 1] = gr;
+      }
+    }
+    for (double v : B) bMax = std::fmax(bMax, std::fabs(v));
+    const double scale = bMax > 0.0 ? 8355711.0 / bMax : 1.0;  // three balanced int8 digits reach +8 355 711
+    scales[ch * 3u] = static_cast<float>(1.0 / scale);
+    scales[ch * 3u + 1u] = static_cast<float>(256.0 / scale);
+    scales[ch * 3u + 2u] = static_cast<float>(65536.0 / scale);
+    for (unsigned m = 0; m < 8; m++) {
+      double re, im;
+      phasor(step * (static_cast<uint64_t>(m) * c->D1), re, im);
+      rot[ch * 8u + m] = make_float2(static_cast<float>(re), static_cast<float>(im));
+    }
+    mods[ch] = cfg->modulations[ch] == B200SDR_MOD_FM ? 1 : 0;
+    c->anyFm = c->anyFm || mods[ch] == 1;
+    gains[ch] = mods[ch] == 1 ? cfg->fm_gains[ch] : 1.0f;
+
+    const unsigned group = ch / kChanNC, local = ch % kChanNC;
+    for (unsigned ks = 0; ks < c->KS; ks++)
+      for (unsigned nt = 0; nt < c->NTC; nt++)
+        for (unsigned half = 0; half < 2; half++)
+          for (unsigned lane = 0; lane < 32; lane++) {
+            const unsigned g = lane >> 2, t = lane & 3u;
+            unsigned word[3] = {0, 0, 0};
+            for (unsigned e = 0; e < 4; e++) {
+              const unsigned k = ks * 32u + half * 16u + t * 4u + e, n = nt * 8u + g;
+              long long q = std::llround(B[static_cast<size_t>(k) * NCOL + n] * scale);
+              for (int d = 0; d < 3; d++) {
+                long long r = ((q % 256) + 256) % 256;
+                if (r >= 128) r -= 256;
+                word[d] |= (static_cast<unsigned>(r) & 0xffu) << (8u * e);
+                q = (q - r) / 256;
+              }
+            }
+            const unsigned n = local * c->NTC + nt;
+            for (unsigned d = 0; d < 3; d++)
+              frag[(static_cast<size_t>(group) * c->KS + ks) * chunkWords + ((n * 3u + d) * 2u + half) * 32u + lane] = word[d];
+          }
+  }
+
+  DeviceGuard guard(c->device);
+  b200sdr_status st = B200SDR_OK;
+  auto upload = [&](const void* host, size_t bytes, void** dev) -> bool {
+    cudaError_t e = cudaMalloc(dev, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      st = cudaFailC(e, "uploading channelizer tables");
+      return false;
+    }
+    return true;
+  };
+  bool ok = guard.status == cudaSuccess;
+  if (!ok) st = cudaFailC(guard.status, "cudaSetDevice");
+  ok = ok && upload(frag.data(), frag.size() * sizeof(unsigned), reinterpret_cast<void**>(&c->dBFrag)) &&
+       upload(rot.data(), rot.size() * sizeof(float2), reinterpret_cast<void**>(&c->dRot)) &&
+       upload(scales.data(), scales.size() * sizeof(float), reinterpret_cast<void**>(&c->dScale)) &&
+       upload(gains.data(), gains.size() * sizeof(float), reinterpret_cast<void**>(&c->dGain)) &&
+       upload(mods.data(), mods.size() * sizeof(int), reinterpret_cast<void**>(&c->dMod)) &&
+       upload(cfg->audio_taps, sizeof(float) * c->T2, reinterpret_cast<void**>(&c->dTaps2));
+  if (!ok) {
+    b200sdr_channelizer_destroy(c);
+    return st;
+  }
+  char buf[200];
+  snprintf(buf, sizeof(buf), "channel<imma,NTC=%u>(channels=%u,groups=%u x %d,warps=%u,rowsTile=%u,kSteps=%u,M=%u) + batched direct FIR", c->NTC,
+           c->C, c->groups, kChanNC, c->warps, c->warps * 32u, c->KS, c->M);
+  c->variant = buf;
+  *out = c;
+  return B200SDR_OK;
+}
+
+B200SDR_EXPORT void b200sdr_channelizer_counts(const b200sdr_channelizer* c, size_t numInputs, size_t* numDemod, size_t* numAudio) {
+  size_t demod = 0, audio = 0;
+  if (c) {
+    const size_t rf = firCount(numInputs, c->T1, c->D1);
+    // every channel uses the FM-safe count (one RF output held back) only if it is FM; per-channel counts differ by one,
+    // so the common count is the smaller one when any channel is FM
+    demod = c->anyFm ? (rf == 0 ? 0 : rf - 1) : rf;
+    audio = firCount(demod, c->T2, c->D2);
+  }
+  if (numDemod) *numDemod = demod;
+  if (numAudio) *numAudio = audio;
+}
+
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
+    b200sdr_channelizer* c, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio, size_t audioStride,
+    size_t numAudio, cudaStream_t stream) {
+  if (!c) return chainFail(B200SDR_INVALID_ARGUMENT, "channelizer is null");
+  if (numAudio == 0) return B200SDR_OK;
+  if (!input || !demodScratch || !audio) return chainFail(B200SDR_INVALID_ARGUMENT, "input/demodScratch/audio is null");
+  if ((reinterpret_cast<uintptr_t>(input) & 15u) != 0) return chainFail(B200SDR_INVALID_ARGUMENT, "input must be 16-byte aligned");
+  const size_t nDemod = (numAudio - 1) * static_cast<size_t>(c->D2) + c->T2;
+  if (demodStride < nDemod || audioStride < numAudio) return chainFail(B200SDR_INVALID_ARGUMENT, "demodStride/audioStride too small");
+  // demod output k reads rows k .. k+M (FM: one more RF output), i.e. input up to (k + 1) * D1 + T1 - 1 at most
+  const size_t needed = (nDemod - 1 + 1) * static_cast<size_t>(c->D1) + c->T1;
+  const size_t neededAm = (nDemod - 1) * static_cast<size_t>(c->D1) + c->T1;
+  if (numInputs < (c->anyFm ? needed : neededAm)) return chainFail(B200SDR_OUT_OF_RANGE, "numAudio outputs need more input samples than numInputs");
+  DeviceGuard guard(c->device);
+  if (guard.status != cudaSuccess) return cudaFailC(guard.status, "cudaSetDevice");
+
+  ChannelParams prm {};
+  prm.in = static_cast<const unsigned char*>(input);
+  prm.out = demodScratch;
+  prm.bFrag = c->dBFrag;
+  prm.rot = c->dRot;
+  prm.digitScale = c->dScale;
+  prm.gain = c->dGain;
+  prm.mod = c->dMod;
+  prm.nIn = numInputs;
+  prm.nOut = nDemod;
+  prm.outStride = demodStride;
+  prm.D1 = c->D1;
+  prm.M = c->M;
+  prm.kSteps = c->KS;
+  prm.numChannels = c->C;
+  const unsigned rowsTile = c->warps * 32u, OT = rowsTile - c->M;
+  const unsigned NT = kChanNC * c->NTC;
+  const size_t ring = static_cast<size_t>(kChanStages) * (static_cast<size_t>(rowsTile) * kChanARow + static_cast<size_t>(NT) * 3u * 64u * 4u);
+  const size_t park = static_cast<size_t>(kChanNC) * c->M * rowsTile * sizeof(float2);
+  const size_t smem = ring > park ? ring : park;
+  const unsigned long long tiles = (nDemod + OT - 1) / OT;
+  if (tiles > 65535ull * 32768ull) return chainFail(B200SDR_OUT_OF_RANGE, "block too long");
+  auto kernel = c->NTC == 1 ? channelKernel<1> : channelKernel<2>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return cudaFailC(e, "cudaFuncSetAttribute");
+  }
+  if (tiles > 65535ull) return chainFail(B200SDR_OUT_OF_RANGE, "more than 65535 row tiles in one call: split the block");
+  kernel<<<dim3(c->groups, static_cast<unsigned>(tiles)), c->warps * 32u, smem, stream>>>(prm);
+  cudaError_t e = launchStatus();
+  if (e != cudaSuccess) return cudaFailC(e, "channelKernel launch");
+
+  FirParams fir {};
+  fir.in = demodScratch;
+  fir.out = audio;
+  fir.taps = c->dTaps2;
+  fir.nOut = numAudio;
+  fir.T = c->T2;
+  fir.D = c->D2;
+  fir.nIn = nDemod;
+  fir.mod = kModNone;
+  fir.gain = 1.0f;
+  fir.inScale = 1.0f;
+  fir.inBatchStride = demodStride;
+  fir.outBatchStride = audioStride;
+  e = launchFirBatched(kElemReal, fir, c->C, stream);
+  if (e != cudaSuccess) return cudaFailC(e, "batched audio FIR launch");
+  return B200SDR_OK;
+}

@@ -115,6 +115,27 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
   return launchStatus();
 }
 
+cudaError_t launchFirBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream) {
+  if (prm.nOut == 0 || batch == 0) return cudaSuccess;
+  if (prm.D == 0) prm.D = 1;
+  if (batch > 65535u) return cudaErrorInvalidConfiguration;
+  prm.M = (prm.T + prm.D - 1) / prm.D;
+  const unsigned outPerBlock = prm.mod == kModFm ? kDirectThreads - 1 : kDirectThreads;
+  const unsigned long long blocks = (prm.nOut + outPerBlock - 1) / outPerBlock;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  const unsigned long long elemBytes = elem == kElemInt8Complex ? 2 : elem == kElemComplex ? 8 : 4;
+  const unsigned long long tileBytes = (static_cast<unsigned long long>(kDirectThreads - 1) * prm.D + prm.T) * elemBytes;
+  const bool staged = tileBytes <= 96 * 1024;
+  const unsigned smemBytes = kDirectFixedSmem + (staged ? static_cast<unsigned>(tileBytes) : 0u);
+  const Kernel k = directKernelFor(elem, false, false, staged);
+  if (smemBytes > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+    if (e != cudaSuccess) return e;
+  }
+  k<<<dim3(static_cast<unsigned>(blocks), batch), kDirectThreads, smemBytes, stream>>>(prm);
+  return launchStatus();
+}
+
 const char* firVariantName(int elem, bool tapsComplex, bool mix, const FirRoute& route, char* buf, size_t bufLen) {
   const char* e = elem == kElemInt8Complex ? "int8c" : elem == kElemComplex ? "cf32" : "f32";
   if (route.rows) {

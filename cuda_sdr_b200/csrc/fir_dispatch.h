@@ -20,6 +20,8 @@ struct FirRoute {
 
 FirRoute planFir(int elem, bool tapsComplex, const void* in, unsigned T, unsigned D, int mod);
 cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaStream_t stream);
+// `batch` independent streams with the given element strides through the direct kernel (one launch, grid.y = batch)
+cudaError_t launchFirBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream);
 const char* firVariantName(int elem, bool tapsComplex, bool mix, const FirRoute& route, char* buf, size_t bufLen);
 uint64_t phaseStepOf(double frequency, double sampleRate);
 

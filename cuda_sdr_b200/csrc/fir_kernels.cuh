@@ -38,6 +38,8 @@ struct FirParams {
   int mod;        // ModKind of the epilogue
   float gain;     // FM
   float inScale;  // 1/128 for int8 input, 1 otherwise
+  // direct kernel only: blockIdx.y selects one of several independent streams (batched audio FIR of the channelizer)
+  unsigned long long inBatchStride, outBatchStride;  // in input / output elements
 };
 
 #ifdef __CUDACC__
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(kDirectThreads) directKernel(const FirParams p
   const unsigned long long nFir = prm.mod == kModFm ? prm.nOut + 1 : prm.nOut;
   const bool active = k < nFir;
   const unsigned long long base = k * prm.D;
-  const Raw* gIn = static_cast<const Raw*>(prm.in);
+  const Raw* gIn = static_cast<const Raw*>(prm.in) + blockIdx.y * prm.inBatchStride;
 
   if constexpr (STAGED) {
     const unsigned long long first = k0 * prm.D;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(kDirectThreads) directKernel(const FirParams p
   }
 
   if constexpr (REALOUT) {
-    if (active) static_cast<float*>(prm.out)[k] = acc.x;
+    if (active) static_cast<float*>(prm.out)[blockIdx.y * prm.outBatchStride + k] = acc.x;
     return;
   }
 
@@ -484,7 +486,9 @@ __global__ void __launch_bounds__(kDirectThreads) directKernel(const FirParams p
   }
   if (tid < outPerBlock && k < prm.nOut) {
     if (MIX && prm.mod == kModNone) carrier = phasorOfTurns(prm.phaseStep * (prm.firstIndex + base));
-    storeDemod(prm.mod, prm.out, k, acc, next, rot1, carrier, prm.gain);
+    void* out = prm.mod == kModNone ? static_cast<void*>(static_cast<float2*>(prm.out) + blockIdx.y * prm.outBatchStride)
+                                    : static_cast<void*>(static_cast<float*>(prm.out) + blockIdx.y * prm.outBatchStride);
+    storeDemod(prm.mod, out, k, acc, next, rot1, carrier, prm.gain);
   }
 }
 

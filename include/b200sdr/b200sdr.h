@@ -122,6 +122,44 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_process_host(
 /* Staging segment size (input samples) used by b200sdr_chain_process_host; default 2^25. */
 B200SDR_EXPORT b200sdr_status b200sdr_chain_set_host_segment(b200sdr_chain* chain, size_t inputSamples);
 
+/* ---- wideband channelizer (BASELINE config C5) --------------------------------------------------- */
+/* Many channels out of ONE wideband int8 IQ stream: per channel mix by its own frequency -> shared RF low-pass
+ * (decimating) -> AM or FM demodulation -> shared audio FIR (decimating).  Equivalent to num_channels instances of the
+ * chain above (i.e. of the reference graph src/filters/factories/RfToPcmAudioFactory.cpp:214-304 behind one
+ * Int8ToFloat) fed with the same input, but the input is read once per group of four channels and the mix + FIR runs
+ * as an int8 GEMM on the tensor cores.  Multi-GPU: every rank builds a channelizer over ITS channels (sharding by
+ * channel, no collective on the filter path). */
+typedef struct b200sdr_channelizer_config {
+  uint32_t struct_size;
+  uint32_t num_channels;
+  double sample_rate;             /* Hz, of the input */
+  const double* frequencies;      /* HOST, per channel: the cosine-source frequency (tuned - channel) */
+  const uint32_t* modulations;    /* HOST, per channel: B200SDR_MOD_AM / B200SDR_MOD_FM */
+  const float* fm_gains;          /* HOST, per channel; ignored for AM channels */
+  const float* rf_taps;           /* HOST, correlation order; shared by all channels */
+  size_t rf_tap_count;
+  size_t rf_decimation;           /* must be a multiple of 8 (16-byte input pieces); ceil(taps / decimation) <= 8 */
+  const float* audio_taps;        /* HOST; shared by all channels */
+  size_t audio_tap_count;
+  size_t audio_decimation;
+  int32_t cuda_device;
+  uint32_t reserved;
+} b200sdr_channelizer_config;
+
+typedef struct b200sdr_channelizer b200sdr_channelizer;
+
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channelizer_config* config, b200sdr_channelizer** out);
+B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* channelizer);
+/* Per-channel output counts for numInputs input samples, by the reference's count rules (as b200sdr_chain_counts). */
+B200SDR_EXPORT void b200sdr_channelizer_counts(const b200sdr_channelizer* channelizer, size_t numInputs, size_t* numDemod, size_t* numAudio);
+/* input: DEVICE int8 IQ (16-byte aligned); demodScratch: DEVICE, num_channels * demodStride floats with
+ * demodStride >= numDemod needed for numAudio outputs ((numAudio-1)*D2 + T2); audio: DEVICE, [channel][audioStride].
+ * Launches: one RF kernel over all channel groups + one batched audio FIR. */
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
+    b200sdr_channelizer* channelizer, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
+    size_t audioStride, size_t numAudio, cudaStream_t stream);
+B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer* channelizer);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* Kernels launched by this library since load (all streams); used by bench.py's gpu_launches. */
 B200SDR_EXPORT uint64_t b200sdr_launch_count(void);

@@ -1,0 +1,90 @@
+"""GPU parity of the wideband channelizer (BASELINE config C5) against the fp64 oracle run channel by channel, called
+through the b200sdr C-ABI; shape and count edge cases; channel sharding equals the unsharded result bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.util import assert_close, assert_fm_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def sdr():
+    import cuda_sdr_b200 as m
+    return m
+
+
+def make(sdr, fs, freqs, mods, T1, D1, T2, D2, dev_hz):
+    t1 = sdr.taps.lowpass(T1, 0.4 * fs / D1, fs)
+    t2 = sdr.taps.lowpass(T2, 0.4 * fs / D1 / D2, fs / D1)
+    gains = [sdr.fm_gain(fs / D1, dev_hz)] * len(freqs)
+    return sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=gains), t1, t2, gains
+
+
+def check(sdr, fs, freqs, mods, T1, D1, T2, D2, n, dev_hz=5e3, seed=3):
+    ch, t1, t2, gains = make(sdr, fs, freqs, mods, T1, D1, T2, D2, dev_hz)
+    x = sdr.synth.int8_iq(n, seed=seed, sample_rate=fs)
+    got = ch.run(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    n_demod, n_audio = ch.counts(n)
+    assert got.shape == (len(freqs), n_audio)
+    for c, (f, m) in enumerate(zip(freqs, mods)):
+        spec = orc.ChainSpec(fs, f, t1, D1, m, gains[c], t2, D2)
+        ref, _, _ = orc.chain(spec, x)
+        # with FM channels present every channel uses the FM count (one RF output held back): an AM channel may be one
+        # audio sample short of its own single-chain count, never more
+        assert n_audio <= ref.size <= n_audio + 1
+        tol = 2e-5 if m == 1 else 1e-5
+        assert_close(got[c], ref[:n_audio], tol=tol, what=f"channel {c} ({'FM' if m else 'AM'}, f={f})")
+    return ch, got
+
+
+def test_small_mixed_channels(sdr):
+    fs = 1.024e6
+    freqs = [-300e3, -111e3, 50e3, 222e3, 333e3, -7e3]
+    mods = [0, 1, 0, 1, 1, 0]
+    check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=200003)
+
+
+def test_few_taps_per_phase_uses_one_n_tile(sdr):
+    fs = 2.0e6
+    ch, _ = check(sdr, fs, [100e3, -400e3, 650e3], [0, 0, 0], T1=101, D1=40, T2=65, D2=10, n=150001)
+    assert "NTC=1" in ch.variant
+
+
+def test_c5_shape_eight_channels(sdr):
+    """C5 per-channel shape (4097 taps, decimate by 640, 273 audio taps, decimate by 5) on an 8-channel slice."""
+    fs = 153.6e6
+    freqs = [(-4 + i) * 600e3 + 37e3 for i in range(8)]
+    mods = [i & 1 for i in range(8)]
+    check(sdr, fs, freqs, mods, T1=4097, D1=640, T2=273, D2=5, n=(1 << 21) + 777, dev_hz=75e3)
+
+
+def test_counts_and_short_inputs(sdr):
+    fs = 1.024e6
+    ch, *_ = make(sdr, fs, [10e3, 20e3], [0, 1], 400, 64, 33, 5, 5e3)
+    for n in (0, 1, 399, 463, 400 + 64 * 40):
+        n_demod, n_audio = ch.counts(n)
+        assert n_audio == orc.chain_num_outputs(n, 400, 64, 1, 33, 5)
+        x = torch.zeros(2 * max(n, 8), dtype=torch.int8, device=DEV)[: 2 * n]
+        assert ch.run(x).shape == (2, n_audio)
+
+
+def test_channel_sharding_is_bit_exact(sdr):
+    """Sharding by channel (the multi-GPU decomposition): each shard's channels equal the same channels of the full set."""
+    from cuda_sdr_b200 import sharding
+    fs = 1.024e6
+    freqs = [(-5 + i) * 90e3 + 1e3 for i in range(11)]
+    mods = [i % 2 for i in range(11)]
+    full, t1, t2, gains = make(sdr, fs, freqs, mods, 400, 64, 33, 5, 5e3)
+    x = torch.from_numpy(sdr.synth.int8_iq(120001, seed=9, sample_rate=fs)).to(DEV)
+    whole = full.run(x)
+    n_audio = whole.shape[1]
+    for world in (2, 4):
+        for rank in range(world):
+            mine = sharding.channels_of_rank(len(freqs), world, rank)
+            part = sdr.Channelizer(fs, [freqs[i] for i in mine], [mods[i] for i in mine], t1, 64, t2, 5,
+                                   fm_gains=[gains[i] for i in mine]).run(x, n_audio)
+            assert torch.equal(part.view(torch.int32), whole[mine].view(torch.int32)), (world, rank)
