@@ -99,6 +99,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
     k<<<static_cast<unsigned>(blocks), kRowsThreads, route.smemBytes, stream>>>(prm);
     return launchStatus();
   }
+  if (envInt("B200SDR_NO_WINDOW", 0) == 0 && windowEligible(elem, tapsComplex, mix, prm)) return launchWindow(elem, prm, stream);
   const unsigned outPerBlock = prm.mod == kModFm ? kDirectThreads - 1 : kDirectThreads;
   const unsigned long long blocks = (prm.nOut + outPerBlock - 1) / outPerBlock;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;

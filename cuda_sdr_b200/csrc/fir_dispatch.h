@@ -24,6 +24,9 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
 cudaError_t launchFirBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream);
 const char* firVariantName(int elem, bool tapsComplex, bool mix, const FirRoute& route, char* buf, size_t bufLen);
 uint64_t phaseStepOf(double frequency, double sampleRate);
+// register-tiled kernel for many taps per kept output (fir_window.cu)
+bool windowEligible(int elem, bool tapsComplex, bool mix, const FirParams& prm);
+cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream);
 
 // rows per thread of the high-RPT variant for MP partial sums (register budget)
 constexpr unsigned rowsRptHigh(unsigned MP) { return MP <= 4 ? 4u : 2u; }

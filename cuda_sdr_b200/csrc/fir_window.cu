@@ -1,0 +1,144 @@
+// windowKernel -- register-tiled decimating FIR for the FFMA-bound cells of the roofline sweep (many taps per kept
+// output: ceil(T / D) > 8), real taps x complex float data (gsdrFirFC) and real x real (gsdrFirFF).
+//
+// Polyphase view: y[k] = sum_p sum_m h[m*D + p] * x[(k + m)*D + p].  For a fixed phase p this is an ordinary (stride-1)
+// FIR of length M = ceil(T/D) over the decimated sequence x_p[q] = x[q*D + p], so one thread that owns R CONSECUTIVE
+// outputs can slide a window of R samples through its registers: per tap one new sample is read from shared memory and
+// R FMAs (packed FFMA2 for complex data) are issued -- an FMA : load ratio of R : 1 instead of the 1 : 1 of a
+// thread-per-output kernel.  The input is staged in shared memory one (phase chunk, tap chunk) at a time, transposed to
+// [phase][q] with one element of padding per R so that the R-strided reads of a warp are conflict-free; every input
+// sample of the CTA's window is read from HBM once.
+#include <gsdr/gsdr.h>
+
+#include "fir_dispatch.h"
+#include "fir_kernels.cuh"
+
+namespace b200sdr {
+
+namespace {
+
+constexpr int kWinThreads = 128;
+constexpr int kWinR = 8;          // consecutive outputs per thread
+constexpr int kWinTapChunk = 32;  // taps (per phase) staged at a time
+constexpr int kWinMaxPhases = 4;  // phases staged at a time (8 measured slower: the 76 KB tile halves the resident CTAs)
+
+template <typename T>
+struct WinTraits;
+template <>
+struct WinTraits<float2> {
+  __device__ static float2 zero() { return make_float2(0.0f, 0.0f); }
+  __device__ static float2 fma(float h, float2 x, float2 acc) { return __ffma2_rn(make_float2(h, h), x, acc); }
+};
+template <>
+struct WinTraits<float> {
+  __device__ static float zero() { return 0.0f; }
+  __device__ static float fma(float h, float x, float acc) { return fmaf(h, x, acc); }
+};
+
+__host__ __device__ constexpr unsigned winPadded(unsigned q) { return q + q / kWinR; }  // one pad element per R
+
+// PC = phases staged together (divides D).  Shared memory: taps [PC][kWinTapChunk] floats, then x [PC][winPadded(rows)] elements.
+template <typename Elem, int PC>
+__global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm) {
+  extern __shared__ __align__(16) unsigned char wsmem[];
+  constexpr unsigned BO = kWinThreads * kWinR;      // outputs per CTA
+  constexpr unsigned ROWS = BO + kWinTapChunk;      // decimated samples staged per phase (window of the tap chunk)
+  constexpr unsigned ROWS_P = winPadded(ROWS) + 1;
+  float* sTaps = reinterpret_cast<float*>(wsmem);
+  Elem* sX = reinterpret_cast<Elem*>(wsmem + PC * kWinTapChunk * sizeof(float));
+
+  const unsigned tid = threadIdx.x;
+  const unsigned D = prm.D, T = prm.T, M = prm.M;
+  const unsigned long long k0 = static_cast<unsigned long long>(blockIdx.x) * BO;  // first output of the CTA
+  const Elem* gIn = static_cast<const Elem*>(prm.in);
+
+  Elem acc[kWinR];
+#pragma unroll
+  for (int r = 0; r < kWinR; r++) acc[r] = WinTraits<Elem>::zero();
+
+  for (unsigned p0 = 0; p0 < D; p0 += PC) {
+    for (unsigned m0 = 0; m0 < M; m0 += kWinTapChunk) {
+      __syncthreads();  // the previous chunk has been consumed
+      // taps of this chunk: sTaps[pc][mm] = h[(m0+mm)*D + p0+pc]
+      for (unsigned i = tid; i < PC * kWinTapChunk; i += kWinThreads) {
+        const unsigned pc = i / kWinTapChunk, mm = i % kWinTapChunk;
+        const unsigned long long j = static_cast<unsigned long long>(m0 + mm) * D + p0 + pc;
+        sTaps[i] = (m0 + mm < M && j < T) ? prm.taps[j] : 0.0f;
+      }
+      // samples: sX[pc][pad(q)] = x[(k0 + m0 + q)*D + p0 + pc],  q < ROWS
+      for (unsigned i = tid; i < ROWS * PC; i += kWinThreads) {
+        const unsigned q = i / PC, pc = i % PC;
+        const unsigned long long idx = (k0 + m0 + q) * D + p0 + pc;
+        sX[pc * ROWS_P + winPadded(q)] = idx < prm.nIn ? gIn[idx] : WinTraits<Elem>::zero();
+      }
+      __syncthreads();
+
+#pragma unroll
+      for (int pc = 0; pc < PC; pc++) {
+        const Elem* xs = sX + pc * ROWS_P;
+        const float* hs = sTaps + pc * kWinTapChunk;
+        const unsigned base = tid * kWinR;  // this thread's first output within the CTA = first sample of its window
+        Elem w[kWinR];
+#pragma unroll
+        for (int r = 0; r < kWinR - 1; r++) w[r] = xs[winPadded(base + r)];
+#pragma unroll
+        for (int mm = 0; mm < kWinTapChunk; mm += kWinR) {
+          float h[kWinR];
+#pragma unroll
+          for (int u = 0; u < kWinR; u += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hs + mm + u);
+            h[u] = hv.x;
+            h[u + 1] = hv.y;
+            h[u + 2] = hv.z;
+            h[u + 3] = hv.w;
+          }
+#pragma unroll
+          for (int u = 0; u < kWinR; u++) {
+            // window slot (u + R - 1) % R receives sample base + mm + u + R - 1; output r uses sample base + r + mm + u
+            w[(u + kWinR - 1) % kWinR] = xs[winPadded(base + mm + u + kWinR - 1)];
+#pragma unroll
+            for (int r = 0; r < kWinR; r++) acc[r] = WinTraits<Elem>::fma(h[u], w[(u + r) % kWinR], acc[r]);
+          }
+        }
+      }
+    }
+  }
+
+  Elem* out = static_cast<Elem*>(prm.out);
+#pragma unroll
+  for (int r = 0; r < kWinR; r++) {
+    const unsigned long long k = k0 + static_cast<unsigned long long>(tid) * kWinR + r;
+    if (k < prm.nOut) out[k] = acc[r];
+  }
+}
+
+template <typename Elem>
+cudaError_t launchWindowT(FirParams prm, cudaStream_t stream) {
+  const unsigned pc = prm.D % 4 == 0 ? 4u : prm.D % 2 == 0 ? 2u : 1u;
+  constexpr unsigned BO = kWinThreads * kWinR, ROWS = BO + kWinTapChunk;
+  const size_t smem = pc * kWinTapChunk * sizeof(float) + static_cast<size_t>(pc) * (winPadded(ROWS) + 1) * sizeof(Elem);
+  const unsigned long long blocks = (prm.nOut + BO - 1) / BO;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  void (*k)(const FirParams) = pc == 4 ? windowKernel<Elem, 4> : pc == 2 ? windowKernel<Elem, 2> : windowKernel<Elem, 1>;
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<static_cast<unsigned>(blocks), kWinThreads, smem, stream>>>(prm);
+  return launchStatus();
+}
+
+}  // namespace
+
+bool windowEligible(int elem, bool tapsComplex, bool mix, const FirParams& prm) {
+  if (tapsComplex || mix || prm.mod != kModNone) return false;
+  if (elem != kElemComplex && elem != kElemReal) return false;
+  return prm.D > 0 && (prm.T + prm.D - 1) / prm.D > 8;  // otherwise the rows / staged direct kernels are the better shape
+}
+
+cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream) {
+  prm.M = (prm.T + prm.D - 1) / prm.D;
+  return elem == kElemComplex ? launchWindowT<float2>(prm, stream) : launchWindowT<float>(prm, stream);
+}
+
+}  // namespace b200sdr
