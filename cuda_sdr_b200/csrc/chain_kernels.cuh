@@ -541,7 +541,9 @@ __global__ void __launch_bounds__(RPT >= 4 ? 192 : RPT == 2 ? 320 : 576, RPT >= 
       o[1] = cMain;
       o[2] = cRest;
       o[3] = cLine;
-      o[4] = tLoop - tEntry;        // prologue
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      o[4] = (static_cast<unsigned long long>(smid) << 40) | static_cast<unsigned long long>(tLoop - tEntry);  // SM id | prologue
       o[5] = clock64() - tEntry;    // whole life of the warp
     }
   } else {

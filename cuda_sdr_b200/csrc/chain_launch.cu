@@ -152,6 +152,14 @@ cudaError_t launchChain(int elem, bool mix, const ChainPlan& plan, ChainParams p
     std::vector<unsigned long long> h(6ull * grid * plan.computeWarps);
     cudaMemcpy(h.data(), prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(prof);
+    if (const char* dump = std::getenv("B200SDR_CHAIN_PROFILE_DUMP")) {  // per (CTA, warp): sm, wait-tile, main, rest, wait-line, total
+      if (FILE* f = fopen(dump, "w")) {
+        for (size_t i = 0; i + 5 < h.size(); i += 6)
+          fprintf(f, "%zu %llu %llu %llu %llu %llu %llu\n", i / 6 / plan.computeWarps, h[i + 4] >> 40, h[i], h[i + 1], h[i + 2], h[i + 3], h[i + 5]);
+        fclose(f);
+      }
+    }
+    for (size_t i = 4; i < h.size(); i += 6) h[i] &= (1ull << 40) - 1;
     double sum[6] = {0, 0, 0, 0, 0, 0}, longest = 0;
     for (size_t i = 0; i < h.size(); i++) {
       sum[i % 6] += static_cast<double>(h[i]);
