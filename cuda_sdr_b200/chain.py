@@ -135,7 +135,7 @@ class Chain:
 
     @property
     def fused(self) -> bool:
-        return self.variant.startswith("chain<")
+        return self.variant.startswith(("chain<", "toeplitz<"))
 
     def process_device(self, x: torch.Tensor, first_index: int = 0, out: torch.Tensor | None = None,
                        scratch: torch.Tensor | None = None) -> torch.Tensor:

@@ -15,6 +15,8 @@
 #include "chain_kernels.cuh"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
+#include "toeplitz_dispatch.h"
+#include "toeplitz_kernels.cuh"
 
 using namespace b200sdr;
 
@@ -82,6 +84,10 @@ struct b200sdr_chain {
   float digitScale[3] = {0.0f, 0.0f, 0.0f};
   FirRoute tableRoute {};       // route the tables were laid out for (aligned input)
   ChainPlan fusedPlan {};       // fused persistent kernel (AM/FM with an audio FIR, aligned input), if the shape allows
+  ToepPlan toepPlan {};         // int8 input: fused kernel whose RF stage is one int8 GEMM over a Toeplitz view of the input
+  uint4* dToepFrag = nullptr;
+  float toepScale[3] = {0.0f, 0.0f, 0.0f};
+  float2 rot1 = make_float2(1.0f, 0.0f);
   std::string variant;
 
   // host-buffer path
@@ -130,6 +136,7 @@ B200SDR_EXPORT void b200sdr_chain_destroy(b200sdr_chain* c) {
   cudaFree(c->dMixTable);
   cudaFree(c->dRotTable);
   cudaFree(c->dBFrag);
+  cudaFree(c->dToepFrag);
   delete c;
 }
 
@@ -268,7 +275,21 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
       return st;
     }
   }
-  if (c->fusedPlan.fused) {
+  if (c->hasAudioFir() && c->elem == kElemInt8Complex) {
+    c->toepPlan = planToeplitz(c->T1, c->D1, c->mod, c->T2, c->D2, c->device);
+    if (c->toepPlan.ok) {
+      std::vector<uint32_t> frag;
+      buildToeplitzFragments(cfg->rf_taps, c->T1, c->D1, c->mix, c->phaseStep, static_cast<double>(c->inScale), c->toepPlan, frag, c->toepScale);
+      if (c->mix) c->rot1 = hostPhasor(c->phaseStep * static_cast<uint64_t>(c->D1));
+      if (!upload(frag.data(), frag.size() * sizeof(uint32_t), reinterpret_cast<void**>(&c->dToepFrag))) {
+        b200sdr_chain_destroy(c);
+        return st;
+      }
+    }
+  }
+  if (c->toepPlan.ok) {
+    c->variant = toeplitzVariantName(c->toepPlan, c->D1, buf, sizeof(buf));
+  } else if (c->fusedPlan.fused) {
     c->variant = chainVariantName(c->elem, c->mix, c->fusedPlan, buf, sizeof(buf));
   } else {
     c->variant = firVariantName(c->elem, false, c->mix, c->tableRoute, buf, sizeof(buf));
@@ -375,6 +396,29 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
     return fail(B200SDR_OUT_OF_RANGE, "numAudio outputs need more input samples than numInputs");
   if (!c->hasAudioFir()) return b200sdr_chain_rf_stage(c, input, numInputs, firstSampleIndex, audio, numAudio, stream);
 
+  if (c->toepPlan.ok && (reinterpret_cast<uintptr_t>(input) & 15u) == 0 && numInputs >= 128) {
+    // one persistent kernel, RF stage on the int8 tensor cores (demodScratch is not touched)
+    DeviceGuard guard(c->device);
+    if (guard.status != cudaSuccess) return cudaFail(guard.status, "cudaSetDevice");
+    ToepParams prm {};
+    prm.in = static_cast<const unsigned char*>(input);
+    prm.out = audio;
+    prm.taps2 = c->dTaps2;
+    prm.bFrag = c->dToepFrag;
+    prm.nInBytes = static_cast<unsigned long long>(numInputs) * 2ull;
+    prm.nAudio = numAudio;
+    prm.D1 = c->D1;
+    prm.T2 = c->T2;
+    prm.D2 = c->D2;
+    prm.fm = c->mod == kModFm ? 1 : 0;
+    prm.gain = c->fmGain;
+    prm.rot1 = c->rot1;
+    prm.s0 = c->toepScale[0];
+    prm.s1 = c->toepScale[1];
+    prm.s2 = c->toepScale[2];
+    CUDA_OR_RETURN(launchToeplitz(c->toepPlan, prm, stream));
+    return B200SDR_OK;
+  }
   if (c->fusedPlan.fused && (reinterpret_cast<uintptr_t>(input) & 15u) == 0) {
     // one persistent kernel: the demodulated stream stays in shared memory (demodScratch is not touched)
     DeviceGuard guard(c->device);

@@ -1,0 +1,409 @@
+// toepKernel -- the int8 -> mix -> decimating FIR -> AM/FM demod -> audio FIR chain as ONE persistent kernel whose RF
+// stage is a dense int8 contraction over a Toeplitz view of the raw input (sm_100a).
+//
+// The decimating FIR with the mixer folded into complex taps c[j] = h[j] * exp(j*w*j) / 128 is
+//     y[k] = sum_j c[j] * z[k*D + j],   z = I + jQ  (the per-output carrier exp(j*w*k*D) drops out of |y| and of the
+//                                                    FM discriminator up to the constant rotation rot1 = exp(j*w*D)).
+// Take the raw byte stream x (I,Q,I,Q,...) and view it as a matrix A whose row i starts at byte i * 8D (four outputs
+// per A-row) and is K = 2*T + 6*D bytes long -- rows overlap, nothing is copied.  With
+//     B[2*(D*n + j) + 0][2n + 0] =  re c[j]    B[2*(D*n + j) + 0][2n + 1] = im c[j]
+//     B[2*(D*n + j) + 1][2n + 0] = -im c[j]    B[2*(D*n + j) + 1][2n + 1] = re c[j]        (n = 0..3, j = 0..T-1)
+// the product (A B)[i][2n + e] is re/im of y[4i + n]: ONE int8 x int8 -> int32 GEMM per tile does convert + mix + FIR +
+// decimate, with no partial sums to exchange and no halo between warps beyond the taps' own overlap.  B is held in 24-bit
+// fixed point as three signed int8 digits (three exact IMMA.16832.S8.S8 per k-step; error <= 2^-24 of the largest entry).
+//
+// Fragment mapping of mma.sync.m16n8k32 (g = lane / 4, t = lane % 4): A-rows are 8D bytes apart, which is 0 or 64 mod 128 --
+// in a dense tile every fragment load would hit the same banks.  The tile is therefore staged by a TMA *tensor* copy with
+// hardware swizzle: the input is described as a 3-D tensor {W bytes, chunk (stride W), shift (stride 16 B)} (W = 64 or
+// 128), so ONE cp.async.bulk.tensor per warp block fetches any 16-byte-aligned run of the stream and lands it densely but
+// XOR-swizzled (address bits [4,6) ^= bits [7,9) for W = 64; [4,7) ^= [7,10) for W = 128).  With that swizzle the eight
+// row addresses of an ldmatrix (320 B apart for D = 40) fall into eight different 16-byte bank groups, and one
+// conflict-free ldmatrix.x4 per (m-tile, k-step) delivers {a0, a1, a2, a3} directly in IMMA register order.
+// The accumulator registers of lane L = 4g + t are exactly outputs L (rows g) and 32 + L (rows g + 8) of the 64-output
+// m-tile: demodulation and the store into the demod line are perfectly coalesced with no shuffle (AM) or one (FM).
+//
+// Division of labour: every compute warp owns a private TMA ring (S slots of one warp block = G m-tiles = 64*G outputs);
+// it refills a slot itself as soon as its k-loop has consumed it, so no warp ever waits for another one to issue a copy.
+// The audio warp(s) turn complete demod lines into audio outputs exactly as in chainKernel (chain_kernels.cuh).
+#pragma once
+
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched from the driver at run time)
+
+#include "chain_kernels.cuh"
+
+namespace b200sdr {
+
+struct ToepParams {
+  const unsigned char* in;  // interleaved int8 I,Q; 16-byte aligned
+  float* out;               // audio outputs
+  const float* taps2;       // T2 audio taps
+  const uint4* bFrag;       // [Q][lane 32][3] : words (ksub*3 + digit)*2 + half of k-steps 2q, 2q+1 (natural k order)
+  unsigned long long nInBytes;
+  unsigned long long nAudio;
+  unsigned D1, T2, D2;
+  unsigned Q, KS;           // pairs of k-steps; k-steps (KS = 2Q or 2Q-1)
+  unsigned NW, NA, S;       // compute warps, audio warps, ring depth per compute warp
+  unsigned slotBytes;       // ring slot stride (multiple of 1024: swizzle atoms)
+  unsigned blockBytes;      // input bytes one warp block reads: (16G-1)*8D + 64Q
+  unsigned boxBytes;        // bytes one tensor copy delivers: blockBytes rounded up to W
+  unsigned wShift;          // log2 W (6 or 7): inner extent of the tensor map = swizzle span
+  unsigned swzMask;         // 0x30 (W = 64) or 0x70 (W = 128): offset ^= (offset >> 3) & swzMask
+  unsigned long long tmaEnd;  // input bytes below this are reachable by the tensor map whatever the shift
+  unsigned dmCapacity;      // floats per demod line
+  int fm;
+  float gain;
+  float2 rot1;              // exp(j*w*D1) (FM only)
+  float s0, s1, s2;         // value = acc0*s0 + acc1*s1 + acc2*s2
+};
+
+struct ToepSmem {
+  unsigned bFragOff, taps2Off, dmOff, slotOff, total;
+};
+
+// barriers: dmFull[2] at 0, dmEmpty[2] at 16, full[NW*S] at 64 (NW*S <= 56)
+__host__ __device__ inline ToepSmem toepSmemLayout(unsigned Q, unsigned T2, unsigned dmCapacity, unsigned NW, unsigned S, unsigned slotBytes) {
+  ToepSmem s;
+  unsigned off = 512;
+  s.bFragOff = off;
+  off += Q * 1536u;
+  s.taps2Off = off;
+  off += ((T2 + 3u) & ~3u) * 4u;
+  s.dmOff = off;
+  off += 2u * dmCapacity * 4u;
+  off = (off + 1023u) & ~1023u;
+  s.slotOff = off;
+  off += NW * S * slotBytes;
+  s.total = off;
+  return s;
+}
+
+#ifdef __CUDACC__
+
+constexpr unsigned kToepMagicBits = 0x4B400000u;  // 1.5 * 2^23: int32 accumulators start here, so their bits ARE the float
+constexpr float kToepMagic = 12582912.0f;
+
+template <int G>
+struct ToepFrag {
+  unsigned a[G][2][4];  // [m-tile][k-step of the pair][a0..a3]
+  uint4 b[3];           // 12 words: (ksub*3 + digit)*2 + half
+};
+
+__device__ __forceinline__ void ldsm4(unsigned (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+template <int G>
+__device__ __forceinline__ void toepMma(int (&acc)[G][3][4], const ToepFrag<G>& f, bool both) {
+  const unsigned w[12] = {f.b[0].x, f.b[0].y, f.b[0].z, f.b[0].w, f.b[1].x, f.b[1].y, f.b[1].z, f.b[1].w, f.b[2].x, f.b[2].y, f.b[2].z, f.b[2].w};
+#pragma unroll
+  for (int j = 0; j < G; j++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) imma16832(acc[j][d], f.a[j][0][0], f.a[j][0][1], f.a[j][0][2], f.a[j][0][3], w[2 * d], w[2 * d + 1]);
+  if (both) {
+#pragma unroll
+    for (int j = 0; j < G; j++)
+#pragma unroll
+      for (int d = 0; d < 3; d++) imma16832(acc[j][d], f.a[j][1][0], f.a[j][1][1], f.a[j][1][2], f.a[j][1][3], w[6 + 2 * d], w[6 + 2 * d + 1]);
+  }
+}
+
+template <int G, bool MAGIC>
+__global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const unsigned NW = prm.NW, NA = prm.NA, S = prm.S;
+  const unsigned D = prm.D1, T2 = prm.T2, D2 = prm.D2;
+  const unsigned fm = prm.fm ? 1u : 0u;
+  const unsigned OTW = 64u * G - fm;  // demod outputs per warp block
+  const unsigned OT = NW * OTW;       // demod outputs per tile
+  const unsigned AS = 8u * D;         // A-row stride (4 outputs)
+  const ToepSmem lay = toepSmemLayout(prm.Q, T2, prm.dmCapacity, NW, S, prm.slotBytes);
+  uint64_t* dmFull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* dmEmpty = reinterpret_cast<uint64_t*>(smem + 16);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 64);
+  const uint4* bFrag = reinterpret_cast<const uint4*>(smem + lay.bFragOff);
+  float* h2 = reinterpret_cast<float*>(smem + lay.taps2Off);
+  float* dm = reinterpret_cast<float*>(smem + lay.dmOff);
+  unsigned char* slots = smem + lay.slotOff;
+
+  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+
+  // ---- this CTA's run of audio outputs ---------------------------------------------------------------
+  const unsigned long long per = prm.nAudio / gridDim.x, extra = prm.nAudio % gridDim.x;
+  const unsigned long long a0 = blockIdx.x * per + (blockIdx.x < extra ? blockIdx.x : extra);
+  const unsigned long long cnt = per + (blockIdx.x < extra ? 1 : 0);
+  if (cnt == 0) return;
+  const unsigned long long row0 = a0 * D2;
+  const unsigned long long needDemod = (cnt - 1) * D2 + T2;
+  const unsigned nTiles = static_cast<unsigned>((needDemod + OT - 1) / OT);
+  const unsigned long long totalBytes = prm.nInBytes;
+  const unsigned char* gin = prm.in;
+  const unsigned blockBytes = prm.blockBytes, slotBytes = prm.slotBytes;
+
+  // ---- prologue ------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (unsigned i = 0; i < NW * S; i++) mbarInit(&full[i], 1);
+    for (unsigned i = 0; i < 2; i++) {
+      mbarInit(&dmFull[i], NW);
+      mbarInit(&dmEmpty[i], NA);
+    }
+    fenceMbarInit();
+  }
+  __syncthreads();
+
+  // byte offset of warp w's block of tile t, and how much of it exists in the input
+  auto blockStart = [&](unsigned t, unsigned w) { return (row0 + static_cast<unsigned long long>(t) * OT + static_cast<unsigned long long>(w) * OTW) * 2ull * D; };
+  // (whole warp) stage the block of tile t into `slot`: one tensor copy, chunk coordinate start / W, shift (start % W) / 16
+  auto issueBlock = [&](unsigned t, unsigned w, unsigned slot) {
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned long long start = blockStart(t, w);
+      fenceProxyAsync();  // this warp's generic-proxy reads of the slot come before the async-proxy write
+      mbarExpectTx(&full[w * S + slot], prm.boxBytes);
+      const int c1 = static_cast<int>(start >> prm.wShift), c2 = static_cast<int>((start & ((1u << prm.wShift) - 1u)) >> 4);
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                       smemAddr(slots + (w * S + slot) * slotBytes)),
+                   "l"(&tmap), "r"(0), "r"(c1), "r"(c2), "r"(smemAddr(&full[w * S + slot]))
+                   : "memory");
+    }
+  };
+  // (whole warp, after the copy has landed) the last bytes of the input lie in a chunk the tensor map cannot reach for
+  // every shift: the copy zero-filled them, put them in by hand
+  auto patchBlock = [&](unsigned t, unsigned w, unsigned slot) {
+    const unsigned long long start = blockStart(t, w);
+    if (start + blockBytes <= prm.tmaEnd || start >= totalBytes) return;
+    const unsigned avail = totalBytes - start < blockBytes ? static_cast<unsigned>(totalBytes - start) : blockBytes;
+    const unsigned from = prm.tmaEnd > start ? static_cast<unsigned>(prm.tmaEnd - start) : 0u;
+    unsigned char* dst = slots + (w * S + slot) * slotBytes;
+    for (unsigned b = from + lane; b < avail; b += 32u) dst[b ^ ((b >> 3) & prm.swzMask)] = gin[start + b];
+    __syncwarp();
+  };
+  if (warp < NW) {
+    for (unsigned t = 0; t < S && t < nTiles; t++) issueBlock(t, warp, t);
+  }
+  {
+    uint4* dst = reinterpret_cast<uint4*>(smem + lay.bFragOff);
+    for (unsigned i = tid; i < prm.Q * 96u; i += blockDim.x) dst[i] = prm.bFrag[i];
+    for (unsigned i = tid; i < ((T2 + 3u) & ~3u); i += blockDim.x) h2[i] = i < T2 ? prm.taps2[i] : 0.0f;
+  }
+  __syncthreads();
+
+  // carry / done bookkeeping is a pure function of the tile index: every warp tracks it on its own
+  unsigned carry = 0;
+  unsigned long long done = 0;
+  const unsigned otDiv = OT / D2, otRem = OT % D2;
+  auto outputsReady = [&](unsigned carryNow) -> unsigned {
+    const unsigned len = carryNow + OT;
+    unsigned nA;
+    if (carryNow + D2 >= T2 && carryNow < T2) {
+      nA = otDiv + (carryNow + otRem >= T2 ? 1u : 0u);  // steady state: no division
+    } else {
+      nA = len >= T2 ? (len - T2) / D2 + 1 : 0;
+    }
+    const unsigned long long left = cnt - done;
+    return static_cast<unsigned long long>(nA) > left ? static_cast<unsigned>(left) : nA;
+  };
+
+  if (warp < NW) {
+    // =========================== compute warps ===========================
+    const unsigned nFull = prm.KS >> 1, odd = prm.KS & 1u, Q = prm.Q;
+    const uint4* bLane = bFrag + lane * 3u;
+    unsigned slot = 0, slotPhase = 0;
+    for (unsigned t = 0; t < nTiles; t++) {
+      mbarWait(&full[warp * S + slot], slotPhase);
+      patchBlock(t, warp, slot);
+      // ldmatrix row offset of this lane in the (unswizzled) block: matrix mi = lane / 8 -> rows +8 for odd mi, k +16 for mi >= 2
+      const uint32_t slotBase = smemAddr(slots + (warp * S + slot) * slotBytes);
+      const unsigned laneOff = ((lane & 7u) + 8u * ((lane >> 3) & 1u)) * AS + 16u * (lane >> 4);
+
+      int acc[G][3][4];
+#pragma unroll
+      for (int j = 0; j < G; j++)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) acc[j][d][e] = MAGIC ? static_cast<int>(kToepMagicBits) : 0;
+
+      // k-step pairs are loaded in order; pair q covers bytes [64q, 64q + 64) of the A-row.  m-tiles are 16*AS = 128*D bytes
+      // apart, a multiple of 1024, so they share the swizzle term.
+      unsigned ldQ = 0;
+      auto loadNext = [&](ToepFrag<G>& f) {
+        const unsigned o0 = laneOff + ldQ * 64u, o1 = o0 + 32u;
+        const uint32_t p0 = slotBase + (o0 ^ ((o0 >> 3) & prm.swzMask)), p1 = slotBase + (o1 ^ ((o1 >> 3) & prm.swzMask));
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+          ldsm4(f.a[j][0], p0 + j * 16u * AS);
+          ldsm4(f.a[j][1], p1 + j * 16u * AS);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) f.b[i] = bLane[ldQ * 96u + i];
+        ldQ++;
+      };
+      ToepFrag<G> f0, f1;
+      loadNext(f0);
+      unsigned q = 0;
+#pragma unroll 1
+      while (q + 2 <= nFull) {
+        loadNext(f1);
+        toepMma<G>(acc, f0, true);
+        if (ldQ < Q) loadNext(f0);
+        toepMma<G>(acc, f1, true);
+        q += 2;
+      }
+      if (q < nFull) {
+        if (odd) loadNext(f1);
+        toepMma<G>(acc, f0, true);
+        if (odd) toepMma<G>(acc, f1, false);
+      } else if (odd) {
+        toepMma<G>(acc, f0, false);
+      }
+
+      // ---- the slot has been consumed (every load fed an IMMA that has issued): refill it -----------------------
+      __syncwarp();
+      if (t + S < nTiles) issueBlock(t + S, warp, slot);
+
+      // ---- digits -> float: outputs lane and 32 + lane of each m-tile --------------------------------------------
+      float2 y[G][2];
+#pragma unroll
+      for (int j = 0; j < G; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float2 v0, v1, v2;
+          if constexpr (MAGIC) {
+            const float2 mC = make_float2(-kToepMagic, -kToepMagic);
+            v0 = __fadd2_rn(make_float2(__int_as_float(acc[j][0][2 * h]), __int_as_float(acc[j][0][2 * h + 1])), mC);
+            v1 = __fadd2_rn(make_float2(__int_as_float(acc[j][1][2 * h]), __int_as_float(acc[j][1][2 * h + 1])), mC);
+            v2 = __fadd2_rn(make_float2(__int_as_float(acc[j][2][2 * h]), __int_as_float(acc[j][2][2 * h + 1])), mC);
+          } else {
+            v0 = make_float2(static_cast<float>(acc[j][0][2 * h]), static_cast<float>(acc[j][0][2 * h + 1]));
+            v1 = make_float2(static_cast<float>(acc[j][1][2 * h]), static_cast<float>(acc[j][1][2 * h + 1]));
+            v2 = make_float2(static_cast<float>(acc[j][2][2 * h]), static_cast<float>(acc[j][2][2 * h + 1]));
+          }
+          y[j][h] = axpy2(prm.s2, v2, axpy2(prm.s1, v1, scale2(prm.s0, v0)));
+        }
+
+      // ---- demodulate into the line (after the audio warp has handed it back) -----------------------------------
+      float dmv[G][2];
+      if (fm) {
+#pragma unroll
+        for (int j = 0; j < G; j++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            // successor of output (j, h, lane): lane + 1 of the same half, or lane 0 of the next half
+            const float2 c = y[j][h];
+            float2 n;
+            n.x = __shfl_down_sync(0xffffffffu, c.x, 1);
+            n.y = __shfl_down_sync(0xffffffffu, c.y, 1);
+            float2 first = make_float2(0.0f, 0.0f);
+            if (h == 0) {
+              first.x = __shfl_sync(0xffffffffu, y[j][1].x, 0);
+              first.y = __shfl_sync(0xffffffffu, y[j][1].y, 0);
+            } else if (j + 1 < G) {
+              first.x = __shfl_sync(0xffffffffu, y[j + 1 < G ? j + 1 : j][0].x, 0);
+              first.y = __shfl_sync(0xffffffffu, y[j + 1 < G ? j + 1 : j][0].y, 0);
+            }
+            if (lane == 31u) n = first;
+            const float2 d = make_float2(fmaf(n.y, c.y, n.x * c.x), fmaf(n.y, c.x, -n.x * c.y));
+            const float2 r = cmulf(d, prm.rot1);
+            dmv[j][h] = prm.gain * atan2f(r.y, r.x);
+          }
+      } else {
+#pragma unroll
+        for (int j = 0; j < G; j++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) dmv[j][h] = sqrtf(fmaf(y[j][h].x, y[j][h].x, y[j][h].y * y[j][h].y));
+      }
+      const unsigned cur = t & 1u, use = t >> 1;
+      if (use > 0) mbarWait(&dmEmpty[cur], (use - 1) & 1u);
+      float* line = dm + cur * prm.dmCapacity + carry + warp * OTW;
+#pragma unroll
+      for (int j = 0; j < G; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const unsigned o = j * 64u + h * 32u + lane;
+          if (o < OTW) line[o] = dmv[j][h];
+        }
+      __syncwarp();
+      if (lane == 0) mbarArrive(&dmFull[cur]);
+
+      // bookkeeping identical to the audio warp's
+      const unsigned nA = outputsReady(carry);
+      done += nA;
+      carry = carry + OT - nA * D2;
+      if (++slot == S) {
+        slot = 0;
+        slotPhase ^= 1u;
+      }
+    }
+  } else {
+    // =========================== audio warp(s) ===========================
+    const bool pairs = (D2 & 1u) == 0;
+    for (unsigned t = 0; t < nTiles; t++) {
+      const unsigned cur = t & 1u, use = t >> 1;
+      mbarWait(&dmFull[cur], use & 1u);
+      const float* line = dm + cur * prm.dmCapacity;
+      const unsigned len = carry + OT;
+      const unsigned nA = outputsReady(carry);
+      // each lane works on outputs o and o + aLanes at once: two independent dot products hide the shared-memory latency
+      const unsigned aLane = (warp - NW) * 32u + lane, aLanes = NA * 32u;
+      for (unsigned o = aLane; o < nA; o += 2u * aLanes) {
+        const bool two = o + aLanes < nA;
+        const float* xa = line + o * D2;
+        const float* xb = two ? xa + aLanes * D2 : xa;
+        float a0s = 0.0f, a1s = 0.0f, a2s = 0.0f, a3s = 0.0f, b0s = 0.0f, b1s = 0.0f, b2s = 0.0f, b3s = 0.0f;
+        unsigned j = 0;
+        if (pairs) {  // o*D2 is even: 64-bit loads of the demod line
+#pragma unroll 2
+          for (; j + 4 <= T2; j += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(h2 + j);
+            const float2 p0 = *reinterpret_cast<const float2*>(xa + j), p1 = *reinterpret_cast<const float2*>(xa + j + 2);
+            const float2 q0 = *reinterpret_cast<const float2*>(xb + j), q1 = *reinterpret_cast<const float2*>(xb + j + 2);
+            a0s = fmaf(hv.x, p0.x, a0s);
+            a1s = fmaf(hv.y, p0.y, a1s);
+            a2s = fmaf(hv.z, p1.x, a2s);
+            a3s = fmaf(hv.w, p1.y, a3s);
+            b0s = fmaf(hv.x, q0.x, b0s);
+            b1s = fmaf(hv.y, q0.y, b1s);
+            b2s = fmaf(hv.z, q1.x, b2s);
+            b3s = fmaf(hv.w, q1.y, b3s);
+          }
+        } else {
+#pragma unroll 2
+          for (; j + 4 <= T2; j += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(h2 + j);
+            a0s = fmaf(hv.x, xa[j], a0s);
+            a1s = fmaf(hv.y, xa[j + 1], a1s);
+            a2s = fmaf(hv.z, xa[j + 2], a2s);
+            a3s = fmaf(hv.w, xa[j + 3], a3s);
+            b0s = fmaf(hv.x, xb[j], b0s);
+            b1s = fmaf(hv.y, xb[j + 1], b1s);
+            b2s = fmaf(hv.z, xb[j + 2], b2s);
+            b3s = fmaf(hv.w, xb[j + 3], b3s);
+          }
+        }
+        for (; j < T2; j++) {
+          a0s = fmaf(h2[j], xa[j], a0s);
+          b0s = fmaf(h2[j], xb[j], b0s);
+        }
+        prm.out[a0 + done + o] = (a0s + a1s) + (a2s + a3s);
+        if (two) prm.out[a0 + done + o + aLanes] = (b0s + b1s) + (b2s + b3s);
+      }
+      const unsigned consumed = nA * D2;
+      const unsigned newCarry = len - consumed;
+      float* next = dm + (cur ^ 1u) * prm.dmCapacity;
+      for (unsigned i = aLane; i < newCarry; i += aLanes) next[i] = line[consumed + i];
+      // every audio warp is done READING this line before any of them starts the next tile, whose carry copy writes it
+      if (NA > 1) {
+        asm volatile("bar.sync 1, %0;" ::"r"(NA * 32u) : "memory");
+      } else {
+        __syncwarp();
+      }
+      if (lane == 0) mbarArrive(&dmEmpty[cur]);
+      done += nA;
+      carry = newCarry;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b200sdr

@@ -1,4 +1,5 @@
-"""GPU parity of the chain -- the fused persistent kernel (chainKernel) and the two-kernel path (K1 =
+"""GPU parity of the chain -- the fused persistent kernels (toepKernel: RF stage as an int8 GEMM over a Toeplitz view of
+the input; chainKernel: polyphase rows) and the two-kernel path (K1 =
 convert+mix+FIR+demod, K2 = audio FIR) -- called through the b200sdr C-ABI, against the fp64 CPU oracle; plus
 size-independent properties at BASELINE sizes."""
 import numpy as np
@@ -64,7 +65,7 @@ def test_c2_am_chain(sdr, n):
     kw = c2_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=12345, what="C2")
-    assert chain.variant.startswith(("chain<int8c,mix=1,MP=3", "rows<int8c,mix=1,MP=3")), chain.variant
+    assert chain.variant.startswith("toeplitz<int8c,G=2"), chain.variant
 
 
 @pytest.mark.parametrize("n", [1 << 20, 654321])
@@ -72,7 +73,7 @@ def test_c3_wbfm_chain(sdr, n):
     kw = c3_spec(sdr)
     x = sdr.synth.int8_iq(n)
     chain, _ = check_chain(sdr, kw, x, n0=99, what="C3")
-    assert chain.variant.startswith(("chain<int8c,mix=1,MP=7", "rows<int8c,mix=1,MP=7")), chain.variant
+    assert chain.variant.startswith(("toeplitz<int8c", "rows<int8c,mix=1,MP=7")), chain.variant
 
 
 def test_none_mode_outputs_mixed_rf_samples_with_absolute_phase(sdr):
@@ -99,8 +100,10 @@ def test_cf32_input_and_no_mixer(sdr, mix, mod):
     check_chain(sdr, kw, x, n0=5, input_int8=False, mix=mix, what=f"cf32 mix={mix} mod={mod}")
 
 
-@pytest.mark.parametrize("T1,D1", [(101, 40), (40, 40), (17, 64), (81, 24), (33, 7), (640, 16), (301, 100)])
-def test_shapes_cover_rows_and_direct_paths(sdr, T1, D1):
+@pytest.mark.parametrize("toeplitz", ["1", "0"])
+@pytest.mark.parametrize("T1,D1", [(101, 40), (40, 40), (17, 64), (81, 24), (33, 7), (640, 16), (301, 100), (3, 8), (1000, 8)])
+def test_shapes_cover_rows_and_direct_paths(sdr, T1, D1, monkeypatch, toeplitz):
+    monkeypatch.setenv("B200SDR_TOEPLITZ", toeplitz)
     fs = 1.0e6
     kw = dict(sample_rate=fs, frequency=-77e3, rf_taps=sdr.taps.lowpass(T1, 0.4 * fs / D1, fs), rf_decim=D1, modulation=sdr.AM,
               audio_taps=sdr.taps.lowpass(21, 0.2 * fs / D1, fs / D1), audio_decim=3)
@@ -120,8 +123,10 @@ def test_empty_and_short_inputs(sdr):
     assert chain.counts(n1)[2] == 1 == orc.chain_num_outputs(n1, 101, 40, 0, 129, 10) and chain.counts(n1 - 1)[2] == 0
 
 
-def test_time_segments_concatenate_bit_exactly(sdr, monkeypatch):
+@pytest.mark.parametrize("toeplitz", ["1", "0"])
+def test_time_segments_concatenate_bit_exactly(sdr, monkeypatch, toeplitz):
     monkeypatch.setenv("B200SDR_FUSED", "1")
+    monkeypatch.setenv("B200SDR_TOEPLITZ", toeplitz)
     """Outputs are a pure function of the absolute sample index: overlapped time segments (the
     multi-GPU and host-staging decomposition) must reproduce the one-shot result bit for bit."""
     kw = c3_spec(sdr)
@@ -130,7 +135,7 @@ def test_time_segments_concatenate_bit_exactly(sdr, monkeypatch):
     x = torch.from_numpy(sdr.synth.int8_iq(n)).to(DEV)
     whole = chain.process_device(x)
     n_audio = whole.numel()
-    assert chain.fused
+    assert chain.fused and chain.variant.startswith("toeplitz<" if toeplitz == "1" else "chain<")
     for parts in (2, 3, 8):
         outs = []
         for i in range(parts):
@@ -169,20 +174,31 @@ def test_two_kernel_path_segments_concatenate_bit_exactly(sdr, monkeypatch):
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_RPT": "1", "B200SDR_CHAIN_WARPS": "12"}, {"B200SDR_FUSED": "1", "B200SDR_CHAIN_AUDIO_WARPS": "3"},
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_MMA": "0", "B200SDR_CHAIN_RPT": "1"},
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "3", "B200SDR_CHAIN_RPT": "2"},
+    {"B200SDR_TOEPLITZ": "1"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_G": "1"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_STAGES": "3"},
+    {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "2"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "8", "B200SDR_TOEP_G": "1"},
+    {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_MAGIC": "0"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_AUDIO_WARPS": "2"},
+    {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_CTAS": "1", "B200SDR_TOEP_WARPS": "3"},
 ])
 @pytest.mark.parametrize("which", ["c2", "c3"])
 def test_every_kernel_variant_matches_the_oracle(sdr, monkeypatch, env, which):
     """Tile shape, ring depth, conversion route and audio split are tuning knobs: each must give the same
     results (to the north-star tolerance) and the same counts."""
+    monkeypatch.setenv("B200SDR_TOEPLITZ", "0")  # the B200SDR_CHAIN_* knobs belong to chainKernel
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     kw = c2_spec(sdr) if which == "c2" else c3_spec(sdr)
     x = sdr.synth.int8_iq(400000 + 17, seed=11)
     chain, _ = check_chain(sdr, kw, x, n0=4242, what=f"{which} {env}")
-    assert chain.fused == (env.get("B200SDR_FUSED") == "1")
+    if env.get("B200SDR_TOEPLITZ") == "1":
+        assert chain.variant.startswith("toeplitz<")
+    else:
+        assert chain.fused == (env.get("B200SDR_FUSED") == "1") and not chain.variant.startswith("toeplitz<")
 
 
-def test_default_route_is_fused_for_c2_and_two_kernels_for_c3(sdr):
+def test_default_routes(sdr, monkeypatch):
+    assert sdr.Chain(**c2_spec(sdr)).variant.startswith("toeplitz<int8c,G=2,magic>")
+    assert sdr.Chain(**c3_spec(sdr)).variant.startswith("toeplitz<int8c,G=1,i2f>")
+    monkeypatch.setenv("B200SDR_TOEPLITZ", "0")
     assert sdr.Chain(**c2_spec(sdr)).variant.startswith("chain<int8c,mix=1,MP=3,RPT=2,conv=imma>")
     assert sdr.Chain(**c3_spec(sdr)).variant.startswith("rows<int8c,mix=1,MP=7")
 
