@@ -60,7 +60,7 @@ struct ToepSmem {
   unsigned bFragOff, taps2Off, dmOff, slotOff, total;
 };
 
-// barriers: dmFull[2] at 0, dmEmpty[2] at 16, full[NW*S] at 64 (NW*S <= 56)
+// barriers: dmFull[2] at 0, dmEmpty[2] at 16, constants at 32, full[NW*S] at 64 (NW*S <= 56)
 __host__ __device__ inline ToepSmem toepSmemLayout(unsigned Q, unsigned T2, unsigned dmCapacity, unsigned NW, unsigned S, unsigned slotBytes) {
   ToepSmem s;
   unsigned off = 512;
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
   const ToepSmem lay = toepSmemLayout(prm.Q, T2, prm.dmCapacity, NW, S, prm.slotBytes);
   uint64_t* dmFull = reinterpret_cast<uint64_t*>(smem);
   uint64_t* dmEmpty = reinterpret_cast<uint64_t*>(smem + 16);
+  uint64_t* constBar = reinterpret_cast<uint64_t*>(smem + 32);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + 64);
   const uint4* bFrag = reinterpret_cast<const uint4*>(smem + lay.bFragOff);
   float* h2 = reinterpret_cast<float*>(smem + lay.taps2Off);
@@ -146,9 +147,10 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
       mbarInit(&dmFull[i], NW);
       mbarInit(&dmEmpty[i], NA);
     }
+    mbarInit(constBar, 1);
     fenceMbarInit();
   }
-  __syncthreads();
+  __syncthreads();  // the only CTA-wide barrier
 
   // byte offset of warp w's block of tile t, and how much of it exists in the input
   auto blockStart = [&](unsigned t, unsigned w) { return (row0 + static_cast<unsigned long long>(t) * OT + static_cast<unsigned long long>(w) * OTW) * 2ull * D; };
@@ -179,13 +181,19 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
   };
   if (warp < NW) {
     for (unsigned t = 0; t < S && t < nTiles; t++) issueBlock(t, warp, t);
+    if (tid == 0) {  // B fragments: one bulk copy, awaited by the compute warps before their first k-loop
+      mbarExpectTx(constBar, prm.Q * 1536u);
+      tmaBulkLoad(smem + lay.bFragOff, prm.bFrag, prm.Q * 1536u, constBar);
+    }
+  } else {  // audio taps: only the audio warps read them
+    const unsigned aTid = tid - NW * 32u;
+    for (unsigned i = aTid; i < ((T2 + 3u) & ~3u); i += NA * 32u) h2[i] = i < T2 ? prm.taps2[i] : 0.0f;
+    if (NA > 1) {
+      asm volatile("bar.sync 1, %0;" ::"r"(NA * 32u) : "memory");
+    } else {
+      __syncwarp();
+    }
   }
-  {
-    uint4* dst = reinterpret_cast<uint4*>(smem + lay.bFragOff);
-    for (unsigned i = tid; i < prm.Q * 96u; i += blockDim.x) dst[i] = prm.bFrag[i];
-    for (unsigned i = tid; i < ((T2 + 3u) & ~3u); i += blockDim.x) h2[i] = i < T2 ? prm.taps2[i] : 0.0f;
-  }
-  __syncthreads();
 
   // carry / done bookkeeping is a pure function of the tile index: every warp tracks it on its own
   unsigned carry = 0;
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
     const unsigned nFull = prm.KS >> 1, odd = prm.KS & 1u, Q = prm.Q;
     const uint4* bLane = bFrag + lane * 3u;
     unsigned slot = 0, slotPhase = 0;
+    mbarWait(constBar, 0);
     for (unsigned t = 0; t < nTiles; t++) {
       mbarWait(&full[warp * S + slot], slotPhase);
       patchBlock(t, warp, slot);
@@ -352,7 +361,33 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
         float a0s = 0.0f, a1s = 0.0f, a2s = 0.0f, a3s = 0.0f, b0s = 0.0f, b1s = 0.0f, b2s = 0.0f, b3s = 0.0f;
         unsigned j = 0;
         if (pairs) {  // o*D2 is even: 64-bit loads of the demod line
-#pragma unroll 2
+          // 16 taps per iteration, every load issued before the first multiply-add: shared-memory latency under load is
+          // ~100 cycles, and this warp is the serial stage of the CTA
+#pragma unroll 1
+          for (; j + 16 <= T2; j += 16) {
+            float4 hv[4];
+            float2 p[4][2], q[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              hv[u] = *reinterpret_cast<const float4*>(h2 + j + 4 * u);
+              p[u][0] = *reinterpret_cast<const float2*>(xa + j + 4 * u);
+              p[u][1] = *reinterpret_cast<const float2*>(xa + j + 4 * u + 2);
+              q[u][0] = *reinterpret_cast<const float2*>(xb + j + 4 * u);
+              q[u][1] = *reinterpret_cast<const float2*>(xb + j + 4 * u + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              a0s = fmaf(hv[u].x, p[u][0].x, a0s);
+              a1s = fmaf(hv[u].y, p[u][0].y, a1s);
+              a2s = fmaf(hv[u].z, p[u][1].x, a2s);
+              a3s = fmaf(hv[u].w, p[u][1].y, a3s);
+              b0s = fmaf(hv[u].x, q[u][0].x, b0s);
+              b1s = fmaf(hv[u].y, q[u][0].y, b1s);
+              b2s = fmaf(hv[u].z, q[u][1].x, b2s);
+              b3s = fmaf(hv[u].w, q[u][1].y, b3s);
+            }
+          }
+#pragma unroll 1
           for (; j + 4 <= T2; j += 4) {
             const float4 hv = *reinterpret_cast<const float4*>(h2 + j);
             const float2 p0 = *reinterpret_cast<const float2*>(xa + j), p1 = *reinterpret_cast<const float2*>(xa + j + 2);
