@@ -313,7 +313,7 @@ def run_ours(args):
             slab_drained[slab].record()
 
     k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    fused = chain.variant.startswith("chain<")
+    fused = chain.fused
 
     def step(i=None, last=False):
         k = step_no[0]
@@ -404,7 +404,8 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         if fused:  # one kernel: 2 B/sample of int8 IQ in, 4 B per audio sample out, nothing in between
             alg_bytes = 2.0 * n + 4.0 * n_audio
-            kernel_name = "chainKernel (convert+mix+FIR+decimate+demod+audio FIR, persistent, one launch per step)"
+            kernel_name = ("toepKernel" if chain.variant.startswith("toeplitz<") else "chainKernel") + \
+                " (convert+mix+FIR+decimate+demod+audio FIR, persistent, one launch per step)"
         else:      # K1 + K2: the demodulated stream makes one round trip through HBM
             alg_bytes = 2.0 * n + 8.0 * n_demod + 4.0 * n_audio
             kernel_name = "rowsKernel + directKernel (two launches per step)"

@@ -86,6 +86,7 @@ struct b200sdr_chain {
   ChainPlan fusedPlan {};       // fused persistent kernel (AM/FM with an audio FIR, aligned input), if the shape allows
   ToepPlan toepPlan {};         // int8 input: fused kernel whose RF stage is one int8 GEMM over a Toeplitz view of the input
   uint4* dToepFrag = nullptr;
+  float* dToepTaps2 = nullptr;  // audio taps zero-padded to a multiple of 4 (one bulk copy in the kernel)
   float toepScale[3] = {0.0f, 0.0f, 0.0f};
   float2 rot1 = make_float2(1.0f, 0.0f);
   std::string variant;
@@ -137,6 +138,7 @@ B200SDR_EXPORT void b200sdr_chain_destroy(b200sdr_chain* c) {
   cudaFree(c->dRotTable);
   cudaFree(c->dBFrag);
   cudaFree(c->dToepFrag);
+  cudaFree(c->dToepTaps2);
   delete c;
 }
 
@@ -281,7 +283,10 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
       std::vector<uint32_t> frag;
       buildToeplitzFragments(cfg->rf_taps, c->T1, c->D1, c->mix, c->phaseStep, static_cast<double>(c->inScale), c->toepPlan, frag, c->toepScale);
       if (c->mix) c->rot1 = hostPhasor(c->phaseStep * static_cast<uint64_t>(c->D1));
-      if (!upload(frag.data(), frag.size() * sizeof(uint32_t), reinterpret_cast<void**>(&c->dToepFrag))) {
+      std::vector<float> taps2((static_cast<size_t>(c->T2) + 3u) & ~static_cast<size_t>(3), 0.0f);
+      for (unsigned i = 0; i < c->T2; i++) taps2[i] = cfg->audio_taps[i];
+      if (!upload(frag.data(), frag.size() * sizeof(uint32_t), reinterpret_cast<void**>(&c->dToepFrag)) ||
+          !upload(taps2.data(), taps2.size() * sizeof(float), reinterpret_cast<void**>(&c->dToepTaps2))) {
         b200sdr_chain_destroy(c);
         return st;
       }
@@ -403,7 +408,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
     ToepParams prm {};
     prm.in = static_cast<const unsigned char*>(input);
     prm.out = audio;
-    prm.taps2 = c->dTaps2;
+    prm.taps2 = c->dToepTaps2;
     prm.bFrag = c->dToepFrag;
     prm.nInBytes = static_cast<unsigned long long>(numInputs) * 2ull;
     prm.nAudio = numAudio;

@@ -62,9 +62,8 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   (void)cudaGetLastError();
 
-  unsigned audioWarps = (T2 / D2 + 15u) / 16u;  // as chainKernel: one warp keeps up with ~16 multiply-adds per demod sample
-  if (audioWarps < 1u) audioWarps = 1u;
-  if (audioWarps > 4u) audioWarps = 4u;
+  // audio warps take tiles in turn; the FIR costs T2/D2 multiply-adds per demodulated sample (C2: 13, WBFM: 55)
+  unsigned audioWarps = T2 / D2 >= 32u ? 4u : 2u;
   const int forcedAudio = envInt("B200SDR_TOEP_AUDIO_WARPS", 0);
   if (forcedAudio >= 1 && forcedAudio <= 4) audioWarps = static_cast<unsigned>(forcedAudio);
   const int forcedG = envInt("B200SDR_TOEP_G", 0), forcedWarps = envInt("B200SDR_TOEP_WARPS", 0);
@@ -78,15 +77,16 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
       if (forcedStages && static_cast<unsigned>(forcedStages) != stages) continue;
       for (unsigned warps : {4u, 8u, 6u, 7u, 5u, 3u, 2u}) {
         if (forcedWarps && static_cast<unsigned>(forcedWarps) != warps) continue;
-        if (warps + audioWarps > 12u || warps * stages > 56u) continue;  // __launch_bounds__(384), barrier table
+        if (warps + audioWarps > 12u || warps * stages > 48u) continue;  // __launch_bounds__(384), barrier table
         const unsigned W = swizzleSpan(D1);
         const unsigned blockBytes = (16u * G - 1u) * AS + 64u * p.Q;
         const unsigned boxBytes = (blockBytes + W - 1u) / W * W;
         if (boxBytes / W > 256u) continue;  // box extent limit of a tensor map
         const unsigned slotBytes = (boxBytes + 1023u) & ~1023u;  // swizzle atoms are 512 / 1024 bytes
         const unsigned OTW = 64u * G - fm, OT = warps * OTW;
-        const unsigned dmCapacity = (OT + T2 + 3u) & ~3u;
-        const ToepSmem lay = toepSmemLayout(p.Q, T2, dmCapacity, warps, stages, slotBytes);
+        const unsigned span = (T2 - 1u + OT - 1u) / OT;  // tiles an audio window reaches back
+        if (span > kToepLines - 2u) continue;
+        const ToepSmem lay = toepSmemLayout(p.Q, T2, OT, warps, stages, slotBytes);
         if (lay.total > kSmemPerSm - kSmemPerCtaReserve) continue;
         unsigned ctas = kSmemPerSm / (lay.total + kSmemPerCtaReserve);
         const unsigned maxByThreads = 2048u / (32u * (warps + audioWarps));
@@ -117,7 +117,7 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
           p.slotBytes = slotBytes;
           p.OTW = OTW;
           p.OT = OT;
-          p.dmCapacity = dmCapacity;
+          p.span = span;
           p.smemBytes = lay.total;
           p.ctasPerSm = ctas;
           p.grid = static_cast<unsigned>(sms) * ctas;
@@ -203,7 +203,7 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   prm.S = plan.S;
   prm.slotBytes = plan.slotBytes;
   prm.blockBytes = plan.blockBytes;
-  prm.dmCapacity = plan.dmCapacity;
+  prm.span = plan.span;
   prm.boxBytes = plan.boxBytes;
   // the input as a tensor {W bytes, chunk (stride W), shift (stride 16 B)}: coordinate (0, s / W, (s % W) / 16) addresses any
   // 16-byte-aligned offset s; chunks are limited so that no shift reads past the end (the kernel patches the last bytes)
@@ -216,12 +216,13 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   const EncodeTiled encode = encodeTiled();
   if (!encode) return cudaErrorNotSupported;
   CUtensorMap tmap;
+  static const int l2promo = envInt("B200SDR_TOEP_L2PROMO", static_cast<int>(CU_TENSOR_MAP_L2_PROMOTION_L2_128B));  // 0 none, 1 64B, 2 128B, 3 256B
   const cuuint64_t gdim[3] = {W, chunks, W / 16u};
   const cuuint64_t gstride[2] = {W, 16u};
   const cuuint32_t box[3] = {W, plan.boxBytes / W, 1u};
   const cuuint32_t estride[3] = {1u, 1u, 1u};
   if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<unsigned char*>(prm.in), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             W == 64u ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             W == 64u ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, static_cast<CUtensorMapL2promotion>(l2promo),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorInvalidValue;
   const ToepKernel k = toepKernelFor(plan.G, plan.magic);

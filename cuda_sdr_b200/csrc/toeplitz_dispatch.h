@@ -18,7 +18,7 @@ struct ToepPlan {
   unsigned G;    // m-tiles (64 outputs each) per warp block
   unsigned Q, KS;
   unsigned NW, NA, S;
-  unsigned blockBytes, boxBytes, slotBytes, OTW, OT, dmCapacity;
+  unsigned blockBytes, boxBytes, slotBytes, OTW, OT, span;
   unsigned smemBytes, ctasPerSm, grid;
 };
 

@@ -14,7 +14,7 @@ python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$?"
 cat $OUT/${TAG}_bench.json
 BENCH_SHORT="python bench.py --steps 5 --warmup 3 --warmup-seconds 0 --skip-e2e --skip-cpu"
-KERNELS='rowsKernel|directKernel|chainKernel|channelKernel'
+KERNELS='rowsKernel|directKernel|chainKernel|channelKernel|toepKernel'
 $BENCH_SHORT > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$KERNELS" -s 6 -c 10 --csv --log-file $OUT/${TAG}_launches.csv \
     $BENCH_SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
