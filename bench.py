@@ -321,10 +321,10 @@ def run_ours(args):
         slab, slot = (k // GATHER_EVERY) & 1, k % GATHER_EVERY
         if world > 1 and slot == 0:
             torch.cuda.current_stream().wait_event(slab_drained[slab])  # this slab's previous gather has drained
-        if i is not None:
+        if i is not None and not fused:
             k1_events[i][0].record()
         got = chain.process_device(x, first_index, out=slabs[slab][slot], scratch=demod)  # fused: ONE kernel; else K1 + K2
-        if i is not None:
+        if i is not None and not fused:
             k1_events[i][1].record()
         assert got.numel() == n_audio
         if slot == GATHER_EVERY - 1 or last:
@@ -366,7 +366,10 @@ def run_ours(args):
     barrier()
     launches = sdr._native.launch_count() - launches0
     total_ms = t_start.elapsed_time(t_end)
-    k1_ms = statistics.mean(a.elapsed_time(b) for a, b in k1_events)
+    # fused route: ONE kernel per step and nothing else on the stream, so the kernel's average duration is the step time
+    # (launch gaps included: an upper bound); events between the launches would serialise what programmatic dependent
+    # launch overlaps.  Two-kernel route: events around K1 + K2 of every step.
+    k1_ms = total_ms / args.steps if fused else statistics.mean(a.elapsed_time(b) for a, b in k1_events)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -82,7 +82,8 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
         const unsigned blockBytes = (16u * G - 1u) * AS + 64u * p.Q;
         const unsigned boxBytes = (blockBytes + W - 1u) / W * W;
         if (boxBytes / W > 256u) continue;  // box extent limit of a tensor map
-        const unsigned slotBytes = (boxBytes + 1023u) & ~1023u;  // swizzle atoms are 512 / 1024 bytes
+        const unsigned atom = W == 64u ? 512u : 1024u;  // the swizzle pattern repeats every 4 / 8 rows of 128 bytes
+        const unsigned slotBytes = (boxBytes + atom - 1u) / atom * atom;
         const unsigned OTW = 64u * G - fm, OT = warps * OTW;
         const unsigned span = (T2 - 1u + OT - 1u) / OT;  // tiles an audio window reaches back
         if (span > kToepLines - 2u) continue;
@@ -125,6 +126,8 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
         if (total >= 8u) return p;
       }
     }
+    // two m-tiles per warp halve the B-fragment traffic per output: keep G = 2 whenever it puts >= 4 warps on an SM
+    if (G == 2u && p.ok && bestWarps >= 4u) return p;
   }
   return p;
 }
@@ -204,6 +207,8 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   prm.slotBytes = plan.slotBytes;
   prm.blockBytes = plan.blockBytes;
   prm.span = plan.span;
+  static const int prefetch = envInt("B200SDR_TOEP_PREFETCH", 0);
+  prm.prefetch = prefetch < 0 ? 0u : static_cast<unsigned>(prefetch);
   prm.boxBytes = plan.boxBytes;
   // the input as a tensor {W bytes, chunk (stride W), shift (stride 16 B)}: coordinate (0, s / W, (s % W) / 16) addresses any
   // 16-byte-aligned offset s; chunks are limited so that no shift reads past the end (the kernel patches the last bytes)
@@ -232,7 +237,20 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   }
   unsigned grid = plan.grid;
   if (static_cast<unsigned long long>(grid) > prm.nAudio) grid = static_cast<unsigned>(prm.nAudio);
-  k<<<grid, 32u * (plan.NW + plan.NA), plan.smemBytes, stream>>>(prm, tmap);
+  // programmatic dependent launch: this kernel's prologue overlaps the tail of the previous kernel in the stream
+  static const bool pdl = envInt("B200SDR_TOEP_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(32u * (plan.NW + plan.NA));
+  cfg.dynamicSmemBytes = plan.smemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1u : 0u;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, prm, tmap);
+  if (e != cudaSuccess) return e;
   return launchStatus();
 }
 

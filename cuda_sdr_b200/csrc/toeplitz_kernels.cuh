@@ -53,6 +53,7 @@ struct ToepParams {
   unsigned wShift;          // log2 W (6 or 7): inner extent of the tensor map = swizzle span
   unsigned swzMask;         // 0x30 (W = 64) or 0x70 (W = 128): offset ^= (offset >> 3) & swzMask
   unsigned long long tmaEnd;  // input bytes below this are reachable by the tensor map whatever the shift
+  unsigned prefetch;        // tiles ahead of the ring's newest slot whose block is prefetched into L2 (0 = off)
   unsigned span;            // tiles before tile t that the audio windows completed by tile t reach into: ceil((T2-1)/OT) <= 2
   int fm;
   float gain;
@@ -163,6 +164,12 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
     tmaBulkLoad(smem + lay.taps2Off, prm.taps2, mirror * 4u, constBar);
   }
   __syncthreads();  // the only CTA-wide barrier
+  // Programmatic dependent launch: everything above touches only this CTA's shared memory and constants written when the
+  // chain was created, so it may overlap the tail of the previous kernel in the stream; the input may be that kernel's
+  // output and the audio buffer may be its input, so every thread waits here before touching either.  (No-ops when the
+  // kernel is launched without the attribute.)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // byte offset of warp w's block of tile t
   auto blockStart = [&](unsigned t, unsigned w) { return (row0 + static_cast<unsigned long long>(t) * OT + static_cast<unsigned long long>(w) * OTW) * 2ull * D; };
@@ -191,8 +198,18 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
     for (unsigned b = from + lane; b < avail; b += 32u) dst[b ^ ((b >> 3) & prm.swzMask)] = gin[start + b];
     __syncwarp();
   };
+  // (lane 0) pull the block of tile t into L2: the ring holds S blocks per warp, L2 extends the pipeline past that at no
+  // cost in shared memory
+  auto prefetchBlock = [&](unsigned t) {
+    if (lane == 0 && t < nTiles) {
+      const unsigned long long start = blockStart(t, warp);
+      const int c1 = static_cast<int>(start >> prm.wShift), c2 = static_cast<int>((start & ((1u << prm.wShift) - 1u)) >> 4);
+      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tmap), "r"(0), "r"(c1), "r"(c2) : "memory");
+    }
+  };
   if (warp < NW) {
     for (unsigned t = 0; t < S && t < nTiles; t++) issueBlock(t, t);
+    for (unsigned t = S; t < S + prm.prefetch; t++) prefetchBlock(t);
   }
 
   // carry / done bookkeeping is a pure function of the tile index: every warp tracks it on its own.  `carry` = demod samples
@@ -270,6 +287,7 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
 
     // ---- the slot has been consumed (every load fed an IMMA that has issued): refill it -----------------------
     if (t + S < nTiles) issueBlock(t + S, slot);
+    if (prm.prefetch) prefetchBlock(t + S + prm.prefetch);
 
     // ---- digits -> float: outputs lane and 32 + lane of each m-tile --------------------------------------------
     float2 y[G][2];

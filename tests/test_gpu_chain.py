@@ -197,7 +197,7 @@ def test_every_kernel_variant_matches_the_oracle(sdr, monkeypatch, env, which):
 
 def test_default_routes(sdr, monkeypatch):
     assert sdr.Chain(**c2_spec(sdr)).variant.startswith("toeplitz<int8c,G=2,magic>")
-    assert sdr.Chain(**c3_spec(sdr)).variant.startswith("toeplitz<int8c,G=1,i2f>")
+    assert sdr.Chain(**c3_spec(sdr)).variant.startswith("toeplitz<int8c,G=2,i2f>")
     monkeypatch.setenv("B200SDR_TOEPLITZ", "0")
     assert sdr.Chain(**c2_spec(sdr)).variant.startswith("chain<int8c,mix=1,MP=3,RPT=2,conv=imma>")
     assert sdr.Chain(**c3_spec(sdr)).variant.startswith("rows<int8c,mix=1,MP=7")

@@ -16,16 +16,11 @@ except Exception as e:
 PY
 }
 timeout 400 python -m pytest tests/test_gpu_chain.py -m gpu -x -q > $OUT/sw_pytest.log 2>&1; tail -4 $OUT/sw_pytest.log
-run am default A=1
-run am aw1 B200SDR_TOEP_AUDIO_WARPS=1
-run am aw3 B200SDR_TOEP_AUDIO_WARPS=3
-run am g1w6 B200SDR_TOEP_G=1 B200SDR_TOEP_WARPS=6
-
-run am w8 B200SDR_TOEP_WARPS=8
-run wbfm fm_default A=1
-run wbfm fm_g2 B200SDR_TOEP_G=2
-run wbfm fm_aw2 B200SDR_TOEP_AUDIO_WARPS=2
-run wbfm fm_g2w4 B200SDR_TOEP_G=2 B200SDR_TOEP_WARPS=4
+run am pdl1 A=1
+run am pdl0 B200SDR_TOEP_PDL=0
+run am pdl1_aw3 B200SDR_TOEP_AUDIO_WARPS=3
+run wbfm fm_pdl1 A=1
+run wbfm fm_pdl0 B200SDR_TOEP_PDL=0
 if [ -n "$NCU" ]; then
 BS="python bench.py --workload am --steps 5 --warmup 3 --warmup-seconds 0 --skip-e2e --skip-cpu"
 ncu --set full --clock-control none --import-source on -k regex:'toepKernel' -s 4 -c 1 -f -o $OUT/${NCU}_prof $BS > $OUT/${NCU}_ncu.log 2>&1
