@@ -91,6 +91,7 @@ B200SDR_SYMBOLS = {
     "b200sdr_launch_count": (u64, []),
     "b200sdr_chain_variant": (C.c_char_p, [vp]),
     "b200sdr_version": (C.c_char_p, []),
+    "b200sdr_toeplitz_tables": (u32, [C.POINTER(f32), sz, sz, u32, f64, f64, C.POINTER(u32), sz, psz, C.POINTER(f32), C.POINTER(u32), C.POINTER(u32)]),
 }
 
 for _name, (_res, _args) in {**GSDR_SYMBOLS, **B200SDR_SYMBOLS}.items():

@@ -117,6 +117,30 @@ B200SDR_EXPORT size_t b200sdr_fir_num_outputs(size_t numInputs, size_t tapCount,
   return firNumOutputs(numInputs, tapCount, decimation);
 }
 
+B200SDR_EXPORT b200sdr_status b200sdr_toeplitz_tables(
+    const float* rfTaps, size_t rfTapCount, size_t rfDecimation, uint32_t mix, double frequency, double sampleRate, uint32_t* fragments,
+    size_t fragCapacityWords, size_t* fragWords, float digitScale[3], uint32_t* kSteps, uint32_t* magic) {
+  if (!rfTaps || rfTapCount == 0 || rfTapCount > (1u << 24) || rfDecimation == 0 || rfDecimation % 8 != 0 || rfDecimation > (1u << 16))
+    return fail(B200SDR_INVALID_ARGUMENT, "rfTaps must be non-null and rfDecimation a multiple of 8");
+  if (mix && !(sampleRate > 0.0)) return fail(B200SDR_INVALID_ARGUMENT, "sample_rate must be positive");
+  ToepPlan plan {};
+  const unsigned T1 = static_cast<unsigned>(rfTapCount), D1 = static_cast<unsigned>(rfDecimation);
+  plan.KS = (2u * T1 + 6u * D1 + 31u) / 32u;
+  plan.Q = (plan.KS + 1u) / 2u;
+  const size_t words = static_cast<size_t>(plan.Q) * 32u * 12u;
+  if (fragWords) *fragWords = words;
+  if (kSteps) *kSteps = plan.KS;
+  if (!fragments) return B200SDR_OK;
+  if (fragCapacityWords < words) return fail(B200SDR_OUT_OF_RANGE, "fragments buffer too small");
+  std::vector<uint32_t> frag;
+  float scale[3];
+  buildToeplitzFragments(rfTaps, T1, D1, mix != 0, mix ? phaseStepOf(frequency, sampleRate) : 0, 1.0 / 128.0, plan, frag, scale);
+  std::memcpy(fragments, frag.data(), words * sizeof(uint32_t));
+  if (digitScale) std::memcpy(digitScale, scale, sizeof(scale));
+  if (magic) *magic = plan.magic ? 1u : 0u;
+  return B200SDR_OK;
+}
+
 B200SDR_EXPORT void b200sdr_chain_destroy(b200sdr_chain* c) {
   if (!c) return;
   DeviceGuard guard(c->device);

@@ -166,5 +166,13 @@ B200SDR_EXPORT uint64_t b200sdr_launch_count(void);
 /* Name of the kernel variant K1 resolves to for this chain ("rows<MP=4,RPT=4,...>" or "direct"). */
 B200SDR_EXPORT const char* b200sdr_chain_variant(const b200sdr_chain* chain);
 B200SDR_EXPORT const char* b200sdr_version(void);
+/* Host-side tables of the Toeplitz chain kernel (csrc/toeplitz_kernels.cuh) for an int8 chain with these RF taps, decimation
+   (a multiple of 8) and mixer: the three-int8-digit fragments of B in the order the kernel reads them
+   ([pair of k-steps q][lane 32][(ksub*3 + digit)*2 + half], one 32-bit word = four k-rows), the digit weights and the
+   number of k-steps.  Needs no GPU; tests/test_toeplitz_tables.py rebuilds B from it and runs the contraction in numpy.
+   fragWords receives the word count; fragments may be NULL to query it. */
+B200SDR_EXPORT b200sdr_status b200sdr_toeplitz_tables(
+    const float* rfTaps, size_t rfTapCount, size_t rfDecimation, uint32_t mix, double frequency, double sampleRate,
+    uint32_t* fragments, size_t fragCapacityWords, size_t* fragWords, float digitScale[3], uint32_t* kSteps, uint32_t* magic);
 
 #endif /* B200SDR_B200SDR_H */
