@@ -165,7 +165,7 @@ def reference_api_rates(wl, log2_samples: int = 24):
     """Throughput of the chain driven through the REFERENCE'S Filter API in <= 1 MiB steps, host buffers in and out
     (oracle/ref/ref_chain.cpp, built by oracle/ref/build_ref.sh into oracle/_ref/):
       reference_cuda_pipeline : the reference's own host framework (compiled in place) + a plain restated gsdr  (= B1)
-      ours_filter_api_fused   : this repo's libgpusdrpipeline.so, the same Filter contract, ONE fused node, 64 MiB steps
+      ours_filter_api_fused   : this repo's libgpusdrpipeline.so, the same Filter contract, ONE fused node, 4 MiB steps
     Returns {} when the binaries are not there (they need /root/reference at build time)."""
     import numpy as np
 
@@ -186,9 +186,9 @@ def reference_api_rates(wl, log2_samples: int = 24):
         runs = [("reference_cuda_pipeline", naive, ["--repeat", "4"],
                  "reference host framework compiled in place + restated one-thread-per-output gsdr kernels (B1), <= 1 MiB steps, "
                  "pinned host in / host out"),
-                ("ours_filter_api_fused", ours, ["--repeat", "16", "--fused", "1", "--step", str(64 << 20)],
+                ("ours_filter_api_fused", ours, ["--repeat", "16", "--fused", "1", "--step", str(4 << 20)],
                  "this repo's libgpusdrpipeline.so through the same Filter contract: CudaMemcpy -> ONE fused node -> CudaMemcpy, "
-                 "64 MiB steps")]
+                 "4 MiB steps")]
         for key, exe, extra, what in runs:
             if not os.path.exists(exe):
                 continue
