@@ -12,6 +12,7 @@
 #include "channel_kernels.cuh"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
+#include "pfb_kernels.cuh"
 
 using namespace b200sdr;
 
@@ -39,6 +40,15 @@ struct b200sdr_channelizer {
   float* dGain = nullptr;
   int* dMod = nullptr;
   float* dTaps2 = nullptr;
+  // polyphase-filter-bank route (pfb_kernels.cuh): every channel on a raster fs/N with one common offset
+  bool pfb = false;
+  unsigned pfbN = 0, pfbQn = 0, pfbSmem = 0;
+  double* dPfbTapsRe = nullptr;
+  double* dPfbTapsIm = nullptr;
+  double2* dPfbAcc0 = nullptr;
+  double2* dPfbTwiddle = nullptr;
+  int* dPfbBin = nullptr;
+  float2* dPfbRot1 = nullptr;
   std::string variant;
 };
 
@@ -51,6 +61,12 @@ B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
   cudaFree(c->dGain);
   cudaFree(c->dMod);
   cudaFree(c->dTaps2);
+  cudaFree(c->dPfbTapsRe);
+  cudaFree(c->dPfbTapsIm);
+  cudaFree(c->dPfbAcc0);
+  cudaFree(c->dPfbTwiddle);
+  cudaFree(c->dPfbBin);
+  cudaFree(c->dPfbRot1);
   delete c;
 }
 
@@ -158,6 +174,58 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
           }
   }
 
+  // ---- polyphase filter bank route: all channel frequencies = f0 + bin * fs / N for a power of two N <= 256 ----
+  std::vector<double2> pfbTaps, pfbAcc0, pfbTwiddle;
+  std::vector<int> pfbBin(c->C, 0);
+  std::vector<float2> pfbRot1(c->C, make_float2(1.0f, 0.0f));
+  {
+    const char* e = std::getenv("B200SDR_PFB");
+    const bool allowed = !(e && std::atoi(e) == 0) && c->C <= kPfbMaxN && c->D1 % 2u == 0;
+    const uint64_t step0 = phaseStepOf(cfg->frequencies[0], cfg->sample_rate);
+    for (unsigned log2N = 2; allowed && !c->pfb && log2N <= 8; log2N++) {
+      const unsigned shift = 64u - log2N;
+      bool fits = true;
+      for (unsigned ch = 0; ch < c->C && fits; ch++) {
+        const uint64_t d = phaseStepOf(cfg->frequencies[ch], cfg->sample_rate) - step0;  // wraps: turns are mod 1
+        const uint64_t b = (d + (1ull << (shift - 1))) >> shift;                          // nearest bin (mod N)
+        const int64_t resid = static_cast<int64_t>(d - (b << shift));
+        fits = resid >= -4096 && resid <= 4096;  // 2^-52 turns: the frequencies were rounded to 2^-64 turns per sample
+        pfbBin[ch] = static_cast<int>(b & ((1ull << log2N) - 1ull));
+      }
+      if (!fits) continue;
+      const unsigned N = 1u << log2N, Qn = (c->T1 + N - 1u) / N;
+      const PfbSmem lay = pfbSmemLayout(N, Qn, c->D1, c->C);
+      if (lay.total > 226u * 1024u) continue;  // a finer raster has fewer taps per phase: keep looking
+      c->pfb = true;
+      c->pfbN = N;
+      c->pfbQn = Qn;
+      c->pfbSmem = lay.total;
+      pfbTaps.assign(static_cast<size_t>(Qn) * N, make_double2(0.0, 0.0));
+      pfbAcc0.assign(N, make_double2(0.0, 0.0));
+      pfbTwiddle.resize(N);
+      for (unsigned j = 0; j < c->T1; j++) {
+        const double phi = twoPi * (static_cast<double>(static_cast<int64_t>(step0 * j)) * (1.0 / 18446744073709551616.0));
+        const double h = static_cast<double>(cfg->rf_taps[j]) * (1.0 / 128.0);
+        pfbTaps[j] = make_double2(h * std::cos(phi), h * std::sin(phi));
+      }
+      const double magic = 1048576.0 + 128.0;  // the kernel feeds X = 2^20 + (x + 128) to the multiply-adds
+      for (unsigned r = 0; r < N; r++) {
+        double sr = 0.0, si = 0.0;
+        for (unsigned q = 0; q < Qn; q++) {
+          sr += pfbTaps[static_cast<size_t>(q) * N + r].x;
+          si += pfbTaps[static_cast<size_t>(q) * N + r].y;
+        }
+        pfbAcc0[r] = make_double2(-magic * (sr - si), -magic * (sr + si));  // -(2^20 + 128) (1 + i) (sr + i si)
+      }
+      for (unsigned t = 0; t < N; t++) pfbTwiddle[t] = make_double2(std::cos(twoPi * t / N), std::sin(twoPi * t / N));
+      for (unsigned ch = 0; ch < c->C; ch++) {
+        const uint64_t step = phaseStepOf(cfg->frequencies[ch], cfg->sample_rate);
+        const double phi = twoPi * (static_cast<double>(static_cast<int64_t>(step * static_cast<uint64_t>(c->D1))) * (1.0 / 18446744073709551616.0));
+        pfbRot1[ch] = make_float2(static_cast<float>(std::cos(phi)), static_cast<float>(std::sin(phi)));
+      }
+    }
+  }
+
   DeviceGuard guard(c->device);
   b200sdr_status st = B200SDR_OK;
   auto upload = [&](const void* host, size_t bytes, void** dev) -> bool {
@@ -177,6 +245,19 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
        upload(gains.data(), gains.size() * sizeof(float), reinterpret_cast<void**>(&c->dGain)) &&
        upload(mods.data(), mods.size() * sizeof(int), reinterpret_cast<void**>(&c->dMod)) &&
        upload(cfg->audio_taps, sizeof(float) * c->T2, reinterpret_cast<void**>(&c->dTaps2));
+  if (ok && c->pfb) {
+    std::vector<double> re(pfbTaps.size()), im(pfbTaps.size());
+    for (size_t i = 0; i < pfbTaps.size(); i++) {
+      re[i] = pfbTaps[i].x;
+      im[i] = pfbTaps[i].y;
+    }
+    ok = upload(re.data(), re.size() * sizeof(double), reinterpret_cast<void**>(&c->dPfbTapsRe)) &&
+         upload(im.data(), im.size() * sizeof(double), reinterpret_cast<void**>(&c->dPfbTapsIm)) &&
+         upload(pfbAcc0.data(), pfbAcc0.size() * sizeof(double2), reinterpret_cast<void**>(&c->dPfbAcc0)) &&
+         upload(pfbTwiddle.data(), pfbTwiddle.size() * sizeof(double2), reinterpret_cast<void**>(&c->dPfbTwiddle)) &&
+         upload(pfbBin.data(), pfbBin.size() * sizeof(int), reinterpret_cast<void**>(&c->dPfbBin)) &&
+         upload(pfbRot1.data(), pfbRot1.size() * sizeof(float2), reinterpret_cast<void**>(&c->dPfbRot1));
+  }
   if (!ok) {
     b200sdr_channelizer_destroy(c);
     return st;
@@ -184,6 +265,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   char buf[200];
   snprintf(buf, sizeof(buf), "channel<imma,NTC=%u>(channels=%u,groups=%u x %d,warps=%u,rowsTile=%u,kSteps=%u,M=%u) + batched direct FIR", c->NTC,
            c->C, c->groups, kChanNC, c->warps, c->warps * 32u, c->KS, c->M);
+  if (c->pfb)
+    snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched direct FIR", c->pfbN, c->C,
+             c->pfbQn, kPfbTileK, kPfbWarps, c->pfbSmem);
   c->variant = buf;
   *out = c;
   return B200SDR_OK;
@@ -218,6 +302,38 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   DeviceGuard guard(c->device);
   if (guard.status != cudaSuccess) return cudaFailC(guard.status, "cudaSetDevice");
 
+  cudaError_t e = cudaSuccess;
+  if (c->pfb) {
+    PfbParams pp {};
+    pp.in = static_cast<const unsigned char*>(input);
+    pp.out = demodScratch;
+    pp.tapsRe = c->dPfbTapsRe;
+    pp.tapsIm = c->dPfbTapsIm;
+    pp.acc0 = c->dPfbAcc0;
+    pp.twiddle = c->dPfbTwiddle;
+    pp.bin = c->dPfbBin;
+    pp.mod = c->dMod;
+    pp.gain = c->dGain;
+    pp.rot1 = c->dPfbRot1;
+    pp.nInBytes = static_cast<unsigned long long>(numInputs) * 2ull;
+    pp.nOut = nDemod;
+    pp.outStride = demodStride;
+    pp.D1 = c->D1;
+    pp.N = c->pfbN;
+    pp.Qn = c->pfbQn;
+    pp.C = c->C;
+    pp.anyFm = c->anyFm ? 1 : 0;
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pfbKernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cudaFailC(e, "cudaFuncSetAttribute");
+    int sms = kSmCount;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const unsigned tileOut = kPfbTileK - (c->anyFm ? 1u : 0u);
+    const unsigned long long pfbTiles = (nDemod + tileOut - 1) / tileOut;
+    const unsigned grid = pfbTiles < static_cast<unsigned long long>(sms) ? static_cast<unsigned>(pfbTiles) : static_cast<unsigned>(sms);
+    pfbKernel<<<grid, kPfbWarps * 32u, c->pfbSmem, stream>>>(pp);
+    e = launchStatus();
+    if (e != cudaSuccess) return cudaFailC(e, "pfbKernel launch");
+  } else {
   ChannelParams prm {};
   prm.in = static_cast<const unsigned char*>(input);
   prm.out = demodScratch;
@@ -247,8 +363,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   }
   if (tiles > 65535ull) return chainFail(B200SDR_OUT_OF_RANGE, "more than 65535 row tiles in one call: split the block");
   kernel<<<dim3(c->groups, static_cast<unsigned>(tiles)), c->warps * 32u, smem, stream>>>(prm);
-  cudaError_t e = launchStatus();
+  e = launchStatus();
   if (e != cudaSuccess) return cudaFailC(e, "channelKernel launch");
+  }
 
   FirParams fir {};
   fir.in = demodScratch;

@@ -72,8 +72,11 @@ def test_counts_and_short_inputs(sdr):
         assert ch.run(x).shape == (2, n_audio)
 
 
-def test_channel_sharding_is_bit_exact(sdr):
-    """Sharding by channel (the multi-GPU decomposition): each shard's channels equal the same channels of the full set."""
+def test_channel_sharding_is_bit_exact(sdr, monkeypatch):
+    """Sharding by channel (the multi-GPU decomposition): each shard's channels equal the same channels of the full set.
+    (Per-channel route: a shard that happens to fit a raster would take the filter bank, whose results agree to the parity
+    tolerance, not bit for bit -- test_filter_bank_equals_direct_route_on_a_shard.)"""
+    monkeypatch.setenv("B200SDR_PFB", "0")
     from cuda_sdr_b200 import sharding
     fs = 1.024e6
     freqs = [(-5 + i) * 90e3 + 1e3 for i in range(11)]
@@ -88,3 +91,41 @@ def test_channel_sharding_is_bit_exact(sdr):
             part = sdr.Channelizer(fs, [freqs[i] for i in mine], [mods[i] for i in mine], t1, 64, t2, 5,
                                    fm_gains=[gains[i] for i in mine]).run(x, n_audio)
             assert torch.equal(part.view(torch.int32), whole[mine].view(torch.int32)), (world, rank)
+
+
+# ---- polyphase-filter-bank route (pfb_kernels.cuh): channels on a raster fs/N with one common offset ----------------------
+@pytest.mark.parametrize("pfb", ["1", "0"])
+@pytest.mark.parametrize("log2n,bins,mods", [
+    (4, [0, 3, 5, 15, 9, 8], [0, 1, 0, 1, 1, 0]),          # N = 16: two radix-4 passes
+    (5, [1, 31, 16, 7], [0, 0, 0, 0]),                    # N = 32: radix-4, radix-4, radix-2; AM only (no successor output)
+    (7, [0, 127, 64, 1, 100, 33, 77], [1, 1, 0, 1, 0, 1, 1]),  # N = 128
+])
+def test_raster_channels_take_the_filter_bank(sdr, monkeypatch, pfb, log2n, bins, mods):
+    monkeypatch.setenv("B200SDR_PFB", pfb)
+    fs, n_fft = 1.024e6, 1 << log2n
+    freqs = [7e3 + b * fs / n_fft for b in bins]  # bins above N/2 are negative frequencies (turns are mod 1)
+    ch, _ = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=200003)
+    assert ch.variant.startswith(f"pfb<N={n_fft},fp64>" if pfb == "1" else "channel<imma"), ch.variant
+
+
+def test_filter_bank_c5_shape_and_empty_channels(sdr):
+    """C5 shape on the 1/256 raster; most of the 24 channels carry no signal at all, so their level is set by what leaks
+    from the strong ones: the bound is relative to each channel's own level."""
+    fs = 153.6e6
+    freqs = [(c - 12) * 600e3 + 100e3 for c in range(24)]
+    mods = [c & 1 for c in range(24)]
+    ch, _ = check(sdr, fs, freqs, mods, T1=4097, D1=640, T2=273, D2=5, n=(1 << 21) + 12345, dev_hz=75e3)
+    assert ch.variant.startswith("pfb<N=256,fp64>"), ch.variant
+
+
+def test_filter_bank_equals_direct_route_on_a_shard(sdr, monkeypatch):
+    """A shard of the raster may resolve to a coarser raster (smaller N): results agree to the parity tolerance."""
+    fs = 1.024e6
+    freqs = [7e3 + b * fs / 64 for b in (0, 8, 16, 40)]  # this subset also fits N = 8
+    mods = [0, 1, 0, 1]
+    ch, got = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=100001)
+    assert ch.variant.startswith("pfb<N=8,fp64>"), ch.variant
+    monkeypatch.setenv("B200SDR_PFB", "0")
+    _, ref = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=100001)
+    for c in range(4):
+        assert_close(got[c], ref[c], tol=2e-5 if mods[c] else 1e-5, what=f"channel {c}")
