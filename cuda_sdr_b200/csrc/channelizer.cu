@@ -266,7 +266,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   snprintf(buf, sizeof(buf), "channel<imma,NTC=%u>(channels=%u,groups=%u x %d,warps=%u,rowsTile=%u,kSteps=%u,M=%u) + batched direct FIR", c->NTC,
            c->C, c->groups, kChanNC, c->warps, c->warps * 32u, c->KS, c->M);
   if (c->pfb)
-    snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched direct FIR", c->pfbN, c->C,
+    snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched audio FIR", c->pfbN, c->C,
              c->pfbQn, kPfbTileK, kPfbWarps, c->pfbSmem);
   c->variant = buf;
   *out = c;
@@ -380,7 +380,13 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   fir.inScale = 1.0f;
   fir.inBatchStride = demodStride;
   fir.outBatchStride = audioStride;
-  e = launchFirBatched(kElemReal, fir, c->C, stream);
+  // many taps per kept output (273 / 5 for C5): the register-tiled window kernel; else the thread-per-output kernel
+  static const bool useWindow = !(std::getenv("B200SDR_AUDIO_WINDOW") && std::atoi(std::getenv("B200SDR_AUDIO_WINDOW")) == 0);
+  fir.M = (fir.T + fir.D - 1) / fir.D;
+  if (useWindow && windowEligible(kElemReal, false, false, fir))
+    e = launchWindowBatched(kElemReal, fir, c->C, stream);
+  else
+    e = launchFirBatched(kElemReal, fir, c->C, stream);
   if (e != cudaSuccess) return cudaFailC(e, "batched audio FIR launch");
   return B200SDR_OK;
 }

@@ -27,6 +27,7 @@ uint64_t phaseStepOf(double frequency, double sampleRate);
 // register-tiled kernel for many taps per kept output (fir_window.cu)
 bool windowEligible(int elem, bool tapsComplex, bool mix, const FirParams& prm);
 cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream);
+cudaError_t launchWindowBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream);
 
 // rows per thread of the high-RPT variant for MP partial sums (register budget)
 constexpr unsigned rowsRptHigh(unsigned MP) { return MP <= 4 ? 4u : 2u; }

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
   const unsigned tid = threadIdx.x;
   const unsigned D = prm.D, T = prm.T, M = prm.M;
   const unsigned long long k0 = static_cast<unsigned long long>(blockIdx.x) * BO;  // first output of the CTA
-  const Elem* gIn = static_cast<const Elem*>(prm.in);
+  const Elem* gIn = static_cast<const Elem*>(prm.in) + blockIdx.y * prm.inBatchStride;  // blockIdx.y: independent streams (batched)
 
   Elem acc[kWinR];
 #pragma unroll
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
     }
   }
 
-  Elem* out = static_cast<Elem*>(prm.out);
+  Elem* out = static_cast<Elem*>(prm.out) + blockIdx.y * prm.outBatchStride;
 #pragma unroll
   for (int r = 0; r < kWinR; r++) {
     const unsigned long long k = k0 + static_cast<unsigned long long>(tid) * kWinR + r;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
 }
 
 template <typename Elem>
-cudaError_t launchWindowT(FirParams prm, cudaStream_t stream) {
+cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
   const unsigned pc = prm.D % 4 == 0 ? 4u : prm.D % 2 == 0 ? 2u : 1u;
   constexpr unsigned BO = kWinThreads * kWinR, ROWS = BO + kWinTapChunk;
   const size_t smem = pc * kWinTapChunk * sizeof(float) + static_cast<size_t>(pc) * (winPadded(ROWS) + 1) * sizeof(Elem);
@@ -124,7 +124,8 @@ cudaError_t launchWindowT(FirParams prm, cudaStream_t stream) {
     const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
   }
-  k<<<static_cast<unsigned>(blocks), kWinThreads, smem, stream>>>(prm);
+  if (batch == 0 || batch > 65535u) return cudaErrorInvalidConfiguration;
+  k<<<dim3(static_cast<unsigned>(blocks), batch), kWinThreads, smem, stream>>>(prm);
   return launchStatus();
 }
 
@@ -136,9 +137,13 @@ bool windowEligible(int elem, bool tapsComplex, bool mix, const FirParams& prm) 
   return prm.D > 0 && (prm.T + prm.D - 1) / prm.D > 8;  // otherwise the rows / staged direct kernels are the better shape
 }
 
-cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream) {
+cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream) { return launchWindowBatched(elem, prm, 1, stream); }
+
+// `batch` independent streams, prm.inBatchStride / prm.outBatchStride elements apart (the channelizer's audio stage)
+cudaError_t launchWindowBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream) {
   prm.M = (prm.T + prm.D - 1) / prm.D;
-  return elem == kElemComplex ? launchWindowT<float2>(prm, stream) : launchWindowT<float>(prm, stream);
+  if (batch == 1) prm.inBatchStride = prm.outBatchStride = 0;
+  return elem == kElemComplex ? launchWindowT<float2>(prm, batch, stream) : launchWindowT<float>(prm, batch, stream);
 }
 
 }  // namespace b200sdr

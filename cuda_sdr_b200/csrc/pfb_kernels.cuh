@@ -100,9 +100,15 @@ __device__ __forceinline__ void pfbFftPass(double2* buf, const double2* tw, unsi
     if (j < count) {
       const unsigned kk = j & (Ns - 1u);
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        v[b][r] = buf[j + r * count];
-        if (r > 0) v[b][r] = cmuld(v[b][r], tw[kk * twStep * r]);
+      for (int r = 0; r < R; r++) v[b][r] = buf[j + r * count];
+      if (Ns > 1u) {  // the first pass has no twiddles; later ones load w and square it (one table read per butterfly)
+        const double2 w1 = tw[kk * twStep];
+        v[b][1] = cmuld(v[b][1], w1);
+        if constexpr (R == 4) {
+          const double2 w2 = cmuld(w1, w1);
+          v[b][2] = cmuld(v[b][2], w2);
+          v[b][3] = cmuld(v[b][3], cmuld(w2, w1));
+        }
       }
     }
   }
