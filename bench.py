@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--log2-block", type=int, default=LOG2_BLOCK, help="log2 of input samples per GPU per step")
     ap.add_argument("--workload", choices=["am", "wbfm", "channelizer"], default="am")
     ap.add_argument("--channels", type=int, default=256, help="channelizer workload: total channels (sharded over the GPUs)")
+    ap.add_argument("--shard", choices=["auto", "channels", "time"], default="auto",
+                    help="channelizer workload, N > 1: shard by channel or by time segment (auto: time on the filter-bank route)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
@@ -478,17 +480,37 @@ def run_channelizer(args):
     n = 1 << log2n
     freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]  # 600 kHz raster
     mods = [c & 1 for c in range(total)]                             # alternating AM / FM
-    mine = sharding.channels_of_rank(total, world, rank)
     t1 = taps.lowpass(T1, 100e3, fs)
     t2 = taps.lowpass(T2, 0.45 * 48e3, fs / D1)
     gain = sdr.fm_gain(fs / D1, 75e3)
-    ch = sdr.Channelizer(fs, [freqs[c] for c in mine], [mods[c] for c in mine], t1, D1, t2, D2, fm_gains=[gain] * len(mine), device=local_rank)
     x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120005)           # identical on every rank: stands in for a broadcast feed
-    n_demod, n_audio = ch.counts(n)
-    scratch = torch.empty(len(mine), (n_audio - 1) * D2 + T2, dtype=torch.float32, device=dev)
+    # Two decompositions, no collective on the filter path either way:
+    #   filter-bank route (all channels on one raster: ONE pass yields every channel) -> overlapped TIME segments, every GPU
+    #     produces all channels for its share of the audio outputs;
+    #   per-channel route -> channel c on rank c mod G, input replicated.
+    probe = sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=[gain] * total, device=local_rank)
+    by_time = probe.variant.startswith("pfb<") and args.shard != "channels"
+    if by_time:
+        mine = list(range(total))
+        ch = probe
+        _, n_audio_total = ch.counts(n)
+        window = sharding.chain_window(T1, D1, T2, any(mods), True)
+        seg = sharding.time_segment(n_audio_total, world, rank, D1 * D2, window)
+        x_mine = x[2 * seg.first_input: 2 * (seg.first_input + seg.input_count)]
+        n_audio = seg.output_count
+        counts_audio = [sharding.time_segment(n_audio_total, world, r, D1 * D2, window).output_count for r in range(world)]
+        shapes = [(total, counts_audio[r]) for r in range(world)]
+    else:
+        mine = sharding.channels_of_rank(total, world, rank)
+        ch = sdr.Channelizer(fs, [freqs[c] for c in mine], [mods[c] for c in mine], t1, D1, t2, D2, fm_gains=[gain] * len(mine), device=local_rank)
+        del probe
+        x_mine = x
+        _, n_audio = ch.counts(n)
+        shapes = [(len(sharding.channels_of_rank(total, world, r)), n_audio) for r in range(world)]
+    n_demod = (n_audio - 1) * D2 + T2
+    scratch = torch.empty(len(mine), n_demod, dtype=torch.float32, device=dev)
     outs = [torch.empty(len(mine), n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
-    counts = [len(sharding.channels_of_rank(total, world, r)) for r in range(world)]
-    gathered = [[torch.empty(counts[r], n_audio, dtype=torch.float32, device=dev) for r in range(world)] for _ in range(2)] \
+    gathered = [[torch.empty(*shapes[r], dtype=torch.float32, device=dev) for r in range(world)] for _ in range(2)] \
         if (world > 1 and rank == 0) else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     done_evt = [torch.cuda.Event() for _ in range(2)]
@@ -503,7 +525,7 @@ def run_channelizer(args):
             torch.cuda.current_stream().wait_event(drained[buf])
         if i is not None:
             k_events[i][0].record()
-        ch.run(x, n_audio, out=outs[buf], scratch=scratch)
+        ch.run(x_mine, n_audio, out=outs[buf], scratch=scratch)
         if i is not None:
             k_events[i][1].record()
         if world > 1:  # gather this step's audio of every rank's channels to rank 0 on the side stream
@@ -528,7 +550,7 @@ def run_channelizer(args):
     t_warm = time.perf_counter()
     warm = 0
     while time.perf_counter() - t_warm < args.warmup_seconds:
-        ch.run(x, n_audio, out=outs[0], scratch=scratch)
+        ch.run(x_mine, n_audio, out=outs[0], scratch=scratch)
         warm += 1
         torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
@@ -560,24 +582,46 @@ def run_channelizer(args):
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         peak = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1590.0
         M = -(-T1 // D1)
-        flops = n * len(mine) * (12.0 + 4.0 * T1 / D1 + 10.0 / D1 + 2.0 * T2 / (D1 * D2))        # ~38 flop / sample / channel
-        executed_ops = 2.0 * (n_demod + M) * (2 * D1) * (16 if M > 4 else 8) * 3 * len(mine)      # int8 MMA ops incl. digits and padding
+        pfb = ch.variant.startswith("pfb<")
+        samples_this_gpu = x_mine.numel() // 2
+        # the per-channel chain costs ~38 flop per input sample per channel; the filter bank does the same job
+        # for all channels at once, so the per-channel figure stays the ALGORITHMIC work the line is normalised by
+        flops = samples_this_gpu * len(mine) * (12.0 + 4.0 * T1 / D1 + 10.0 / D1 + 2.0 * T2 / (D1 * D2))
+        hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        if pfb:
+            # bytes the two launches must move: int8 IQ in, demodulated samples out and back in, audio out
+            alg_bytes = 2.0 * samples_this_gpu + len(mine) * (8.0 * n_demod + 4.0 * n_audio)
+            roofline = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                        "kernel": "pfbKernel (polyphase filter bank + fp64 FFT + demod, all channels) + batched audio FIR (windowKernel)",
+                        "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                        "per_channel_equivalent_tflops": flops / (k_ms * 1e-3) / 1e12,
+                        "note": "the filter bank replaces ~38 flop per sample PER CHANNEL by ~60 flop per sample for all channels, so the "
+                                "binding roof is HBM (2 B per sample in + the demodulated streams); today the kernel is bound by FP64 "
+                                "latency at 8 warps per SM (DESIGN.md)"}
+        else:
+            executed_ops = 2.0 * (n_demod + M) * (2 * D1) * (16 if M > 4 else 8) * 3 * len(mine)      # int8 MMA ops incl. digits and padding
+            roofline = {"bound": "tensor", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                        "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                        "kernel": "channelKernel (int8 GEMM RF stage + demod) + batched audio FIR", "kernel_ms": k_ms,
+                        "algorithmic_flops_per_launch": flops, "executed_int8_tops": executed_ops / (k_ms * 1e-3) / 1e12,
+                        "legacy_imma_peak_tops_measured": 1143.0,
+                        "note": "algorithmic flops (SURVEY 8(d): ~38 per sample per channel) against the measured bf16 GEMM peak; the kernel "
+                                "executes the contraction as 3 int8 digit MMAs on the legacy IMMA path (tools/imma_bench.cu: 1143 TOP/s on this part)"}
         line = {
             "metric": "input Msps through the 256-channel wideband channelizer (int8 -> mix -> FIR -> AM/FM demod -> audio FIR per channel)",
             "value": n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8 x s8 -> s32 (24-bit fixed-point taps), f32 epilogue",
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 filter bank + FFT, f32 demod / audio FIR" if pfb else "s8 x s8 -> s32 (24-bit fixed-point taps), f32 epilogue",
             "data": "synthetic",
             "config": {"workload": f"C5 wideband channelizer: 2^{log2n} int8 IQ samples per step at 153.6 Msps-class rate, {total} channels on a 600 kHz "
                                    f"raster alternating AM/FM, per channel mix -> {T1}-tap FIR /{D1} -> demod -> {T2}-tap audio FIR /{D2}",
-                       "channels_total": total, "channels_this_gpu": len(mine), "samples_per_step": n,
-                       "parallelism": "channels interleaved over the GPUs (c mod G), input replicated; NCCL send/recv gather of the audio to rank 0 on a side stream",
+                       "channels_total": total, "channels_this_gpu": len(mine), "samples_per_step": n, "samples_this_gpu": samples_this_gpu,
+                       "parallelism": ("overlapped time segments of the wideband stream, every GPU produces all channels for its share of the audio outputs"
+                                       if by_time else "channels interleaved over the GPUs (c mod G), input replicated") +
+                                      "; NCCL send/recv gather of the audio to rank 0 on a side stream",
                        "l2": f"input block {2 * n >> 20} MiB exceeds the 126 MB L2", "kernel_variant": ch.variant},
-            "roofline": {"bound": "tensor", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops / (k_ms * 1e-3) / 1e12 / peak,
-                         "traffic": None, "kernel": "channelKernel (int8 GEMM RF stage + demod) + batched audio FIR", "kernel_ms": k_ms,
-                         "algorithmic_flops_per_launch": flops, "executed_int8_tops": executed_ops / (k_ms * 1e-3) / 1e12,
-                         "legacy_imma_peak_tops_measured": 1143.0,
-                         "note": "algorithmic flops (SURVEY 8(d): ~38 per sample per channel) against the measured bf16 GEMM peak; the kernel executes "
-                                 "the contraction as 3 int8 digit MMAs on the legacy IMMA path (tools/imma_bench.cu: 1143 TOP/s on this part)"},
+            "roofline": roofline,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -129,3 +129,28 @@ def test_filter_bank_equals_direct_route_on_a_shard(sdr, monkeypatch):
     _, ref = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=100001)
     for c in range(4):
         assert_close(got[c], ref[c], tol=2e-5 if mods[c] else 1e-5, what=f"channel {c}")
+
+
+def test_filter_bank_time_segments_concatenate_bit_exactly(sdr):
+    """The multi-GPU decomposition of the filter-bank route: overlapped time segments of the wideband stream, all channels
+    per segment.  Every RF output is a function of its own input window only, so segments equal the one-shot result."""
+    from cuda_sdr_b200 import sharding
+    fs, T1, D1, T2, D2 = 1.024e6, 400, 64, 33, 5
+    bins = [0, 3, 5, 15, 9, 8, 12]
+    mods = [0, 1, 0, 1, 1, 0, 1]
+    freqs = [7e3 + b * fs / 16 for b in bins]
+    ch, t1, t2, gains = make(sdr, fs, freqs, mods, T1, D1, T2, D2, 5e3)
+    assert ch.variant.startswith("pfb<N=16")
+    n = 300007
+    x = torch.from_numpy(sdr.synth.int8_iq(n, seed=21, sample_rate=fs)).to(DEV)
+    whole = ch.run(x)
+    n_audio = whole.shape[1]
+    window = sharding.chain_window(T1, D1, T2, True, True)
+    for parts in (2, 3, 8):
+        cols = []
+        for i in range(parts):
+            seg = sharding.time_segment(n_audio, parts, i, D1 * D2, window)
+            cols.append(ch.run(x[2 * seg.first_input: 2 * (seg.first_input + seg.input_count)], seg.output_count))
+        cat = torch.cat(cols, dim=1)
+        assert cat.shape == whole.shape
+        assert torch.equal(cat.view(torch.int32), whole.view(torch.int32)), parts
