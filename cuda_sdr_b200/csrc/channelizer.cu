@@ -48,6 +48,7 @@ struct b200sdr_channelizer {
   double2* dPfbAcc0 = nullptr;
   double2* dPfbTwiddle = nullptr;
   int* dPfbBin = nullptr;
+  int* dPfbOrder = nullptr;
   float2* dPfbRot1 = nullptr;
   std::string variant;
 };
@@ -66,6 +67,7 @@ B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
   cudaFree(c->dPfbAcc0);
   cudaFree(c->dPfbTwiddle);
   cudaFree(c->dPfbBin);
+  cudaFree(c->dPfbOrder);
   cudaFree(c->dPfbRot1);
   delete c;
 }
@@ -246,6 +248,10 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
        upload(mods.data(), mods.size() * sizeof(int), reinterpret_cast<void**>(&c->dMod)) &&
        upload(cfg->audio_taps, sizeof(float) * c->T2, reinterpret_cast<void**>(&c->dTaps2));
   if (ok && c->pfb) {
+    std::vector<int> pfbOrder;  // AM channels first, then FM: a warp demodulates 32 channels of one kind per instruction
+    for (int kind = 0; kind < 2; kind++)
+      for (unsigned ch = 0; ch < c->C; ch++)
+        if (mods[ch] == kind) pfbOrder.push_back(static_cast<int>(ch));
     std::vector<double> re(pfbTaps.size()), im(pfbTaps.size());
     for (size_t i = 0; i < pfbTaps.size(); i++) {
       re[i] = pfbTaps[i].x;
@@ -256,6 +262,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
          upload(pfbAcc0.data(), pfbAcc0.size() * sizeof(double2), reinterpret_cast<void**>(&c->dPfbAcc0)) &&
          upload(pfbTwiddle.data(), pfbTwiddle.size() * sizeof(double2), reinterpret_cast<void**>(&c->dPfbTwiddle)) &&
          upload(pfbBin.data(), pfbBin.size() * sizeof(int), reinterpret_cast<void**>(&c->dPfbBin)) &&
+         upload(pfbOrder.data(), pfbOrder.size() * sizeof(int), reinterpret_cast<void**>(&c->dPfbOrder)) &&
          upload(pfbRot1.data(), pfbRot1.size() * sizeof(float2), reinterpret_cast<void**>(&c->dPfbRot1));
   }
   if (!ok) {
@@ -312,6 +319,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
     pp.acc0 = c->dPfbAcc0;
     pp.twiddle = c->dPfbTwiddle;
     pp.bin = c->dPfbBin;
+    pp.order = c->dPfbOrder;
     pp.mod = c->dMod;
     pp.gain = c->dGain;
     pp.rot1 = c->dPfbRot1;

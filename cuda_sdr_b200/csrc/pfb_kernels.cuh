@@ -43,6 +43,8 @@ struct PfbParams {
   const double2* acc0;          // [N]
   const double2* twiddle;       // exp(+2*pi*i*t/N), t < N
   const int* bin;               // [C] FFT bin of each channel
+  const int* order;             // [C] channel indices sorted by modulation: lane i of a warp handles order[i + 32*slot], so a warp
+                                //     instruction demodulates 32 channels of ONE kind (no AM / FM divergence)
   const int* mod;               // [C] 0 AM, 1 FM
   const float* gain;            // [C]
   const float2* rot1;           // [C] exp(j*w_c*D)
@@ -168,18 +170,20 @@ __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams p
     tw[i] = prm.twiddle[i];
   }
 
-  // the channels of this lane (ch = lane + 32 * slot) and their constants live in registers for the whole kernel
+  // the channels of this lane (order[lane + 32 * slot]) and their constants live in registers for the whole kernel
   constexpr int kSlots = kPfbMaxN / 32;
-  int binL[kSlots], modL[kSlots];
+  int chL[kSlots], binL[kSlots], modL[kSlots];
   float gainL[kSlots];
   float2 rotL[kSlots];
 #pragma unroll
   for (int slot = 0; slot < kSlots; slot++) {
-    const unsigned ch = lane + 32u * slot;
-    binL[slot] = ch < C ? prm.bin[ch] : 0;
-    modL[slot] = ch < C ? prm.mod[ch] : 0;
-    gainL[slot] = ch < C ? prm.gain[ch] : 0.0f;
-    rotL[slot] = ch < C ? prm.rot1[ch] : make_float2(1.0f, 0.0f);
+    const unsigned i = lane + 32u * slot;
+    const int ch = i < C ? prm.order[i] : -1;
+    chL[slot] = ch;
+    binL[slot] = ch >= 0 ? prm.bin[ch] : 0;
+    modL[slot] = ch >= 0 ? prm.mod[ch] : 0;
+    gainL[slot] = ch >= 0 ? prm.gain[ch] : 0.0f;
+    rotL[slot] = ch >= 0 ? prm.rot1[ch] : make_float2(1.0f, 0.0f);
   }
 
   const unsigned tileOut = kPfbTileK - (fm ? 1u : 0u);  // demodulated samples a tile yields
@@ -303,8 +307,8 @@ __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams p
         const double2* prevBuf = warp > 0 ? buf - N : nullptr;
 #pragma unroll
         for (int slot = 0; slot < kSlots; slot++) {
-          const unsigned ch = lane + 32u * slot;
-          if (ch < C) {
+          if (chL[slot] >= 0) {
+            const unsigned ch = static_cast<unsigned>(chL[slot]);
             const double2 yd = buf[binL[slot]];
             if (modL[slot] == 0) {
               {
@@ -330,8 +334,8 @@ __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams p
       if (fm && warp == kPfbWarps - 1u && k < nRf) {  // this round's last output is the next round's first predecessor
 #pragma unroll
         for (int slot = 0; slot < kSlots; slot++) {
-          const unsigned ch = lane + 32u * slot;
-          if (ch < C) {
+          if (chL[slot] >= 0) {
+            const unsigned ch = static_cast<unsigned>(chL[slot]);
             const double2 yd = buf[binL[slot]];
             lastY[((round + 1u) & 1u) * C + ch] = make_float2(static_cast<float>(yd.x), static_cast<float>(yd.y));
           }
