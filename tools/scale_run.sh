@@ -5,7 +5,7 @@ OUT=gpurun_out/scale
 mkdir -p $OUT
 for N in 1 2 4 8; do
   for WL in am channelizer; do
-    STEPS=$([ $WL = am ] && echo 200 || echo 10)
+    STEPS=$([ $WL = am ] && echo 200 || echo 20)
     if [ $N = 1 ]; then
       timeout -k 5 200 python bench.py --workload $WL --steps $STEPS --warmup 5 --skip-cpu > $OUT/${WL}_n$N.json 2> $OUT/${WL}_n$N.err
     else
