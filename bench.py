@@ -289,7 +289,7 @@ def run_ours(args):
     # Audio of GATHER_EVERY consecutive steps is collected in one of two slabs; a full slab is gathered to rank 0 with ONE
     # batched send/recv on a side stream while the next slab fills (the exchange is ~1 % of the input bytes: what it costs
     # is host-side enqueue time per call, hence the batching)
-    GATHER_EVERY = 8
+    GATHER_EVERY = int(os.environ.get("BENCH_GATHER_EVERY", "32"))  # measured at N = 2: 8 -> 0.1065, 32 -> 0.1043, 64 -> 0.1042 ms/step
     slabs = [torch.empty(GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
     first_index = rank * n  # absolute sample index of the segment (mixer phase)
     gathered = [torch.empty(world, GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
@@ -476,7 +476,7 @@ def run_channelizer(args):
 
     fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5            # 153.6 Msps = 48 kHz x 640 x 5
     total = args.channels
-    log2n = args.log2_block if args.log2_block != LOG2_BLOCK else 27
+    log2n = args.log2_block if args.log2_block != LOG2_BLOCK else 29  # 3.5 s of signal per step: long segments amortise the per-launch costs at N = 8
     n = 1 << log2n
     freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]  # 600 kHz raster
     mods = [c & 1 for c in range(total)]                             # alternating AM / FM

@@ -25,4 +25,13 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"$KERNELS" -s 6 -c 2 \
     -f -o $OUT/${TAG}_prof $BENCH_SHORT > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
-ls -la $OUT | tail -20
+
+# the channelizer workload (C5): bench line + ncu --set full of its two kernels (short block for the capture)
+python bench.py --workload channelizer --steps 20 --warmup 3 --skip-cpu > $OUT/${TAG}_bench_c5.json 2> $OUT/${TAG}_bench_c5.err
+echo "bench c5 rc=$?"
+python bench.py --workload wbfm --steps 200 --warmup 5 --skip-cpu --skip-e2e > $OUT/${TAG}_bench_c3.json 2> $OUT/${TAG}_bench_c3.err
+echo "bench c3 rc=$?"
+C5_SHORT="python bench.py --workload channelizer --log2-block 27 --steps 3 --warmup 3 --warmup-seconds 0 --skip-cpu"
+ncu --set full --clock-control none --import-source on -k regex:'pfbKernel|windowKernel' -s 6 -c 2 \
+    -f -o $OUT/${TAG}_prof_c5 $C5_SHORT > $OUT/${TAG}_ncu_full_c5.log 2>&1
+echo "ncu c5 rc=$?"
