@@ -59,6 +59,8 @@ struct Args {
   string mod = "am", taps1, taps2, in, out;
   size_t d1 = 1, d2 = 1, repeat = 1, step = 1 << 20;
   bool fused = false;
+  string rftopcm;  // "api": IRfToPcmAudioFactory::createRfToPcm (cf32 input); "json": createFilter("RfToPcmAudio", ...) with int8 input
+  double channelWidth = 10e3, tuned = 0.0;
 };
 
 static Args parse(int argc, char** argv) {
@@ -78,12 +80,16 @@ static Args parse(int argc, char** argv) {
     else if (k == "--repeat") a.repeat = strtoull(v.c_str(), nullptr, 10);
     else if (k == "--step") a.step = strtoull(v.c_str(), nullptr, 10);
     else if (k == "--fused") a.fused = v != "0";
+    else if (k == "--rftopcm") a.rftopcm = v;
+    else if (k == "--channel-width") a.channelWidth = atof(v.c_str());
+    else if (k == "--tuned") a.tuned = atof(v.c_str());
     else {
       fprintf(stderr, "unknown argument %s\n", k.c_str());
       exit(2);
     }
   }
-  if (a.taps1.empty() || a.taps2.empty() || a.in.empty()) {
+  if (!a.rftopcm.empty()) a.fused = true;  // the factory designs its own taps
+  if ((a.rftopcm.empty() && (a.taps1.empty() || a.taps2.empty())) || a.in.empty()) {
     fprintf(stderr, "--taps1, --taps2 and --in are required\n");
     exit(2);
   }
@@ -98,11 +104,15 @@ int main(int argc, char** argv) {
   const Args a = parse(argc, argv);
   gslogSetVerbosity(GSLOG_WARN);
   const vector<char> input = readFile(a.in);
-  const vector<float> taps1 = readFloats(a.taps1), taps2 = readFloats(a.taps2);
+  const vector<float> taps1 = a.taps1.empty() ? vector<float>() : readFloats(a.taps1), taps2 = a.taps2.empty() ? vector<float>() : readFloats(a.taps2);
   const bool fm = a.mod == "fm";
 
   ConstRef<IFactories> factories = unwrap(getFactoriesSingleton());
-  ConstRef<ICudaCommandQueue> queue = unwrap(factories->getCudaCommandQueueFactory()->create(0));
+  // --rftopcm: the declarative route names its queue (applications/nbfm_test.cpp:546-562); every node of the graph, the
+  // copy filters included, must then run on that queue
+  if (!a.rftopcm.empty()) THROW_IF_ERR(factories->getCommandQueueFactory()->create("q0", "{\"queueType\": \"cuda\", \"cudaDevice\": 0}"));
+  ConstRef<ICudaCommandQueue> queue = a.rftopcm.empty() ? unwrap(factories->getCudaCommandQueueFactory()->create(0))
+                                                        : unwrap(factories->getCommandQueueFactory()->getCudaCommandQueue("q0"));
   const float rfRate = static_cast<float>(a.fs);
   const float demodRate = static_cast<float>(a.fs / static_cast<double>(a.d1));
 
@@ -111,36 +121,66 @@ int main(int argc, char** argv) {
     // host int8 -> CudaMemcpy (pinned, H2D) -> ONE fused node -> CudaMemcpy (D2H) -> host float, same Filter contract
     ConstRef<Filter> h2d = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyHostToDevice, queue));
     ConstRef<Filter> d2h = unwrap(factories->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyDeviceToHost, queue));
-    GsFusedChainParams p {};
-    p.structSize = sizeof(p);
-    p.inputType = SampleType_Int8Complex;
-    p.modulation = fm ? Modulation_Fm : Modulation_Am;
-    p.mix = 1;
-    p.sampleRate = a.fs;
-    p.frequency = a.freq;
-    p.rfTaps = taps1.data();
-    p.rfTapCount = taps1.size();
-    p.rfDecimation = a.d1;
-    p.fmGain = demodRate / (2.0f * static_cast<float>(M_PI) * static_cast<float>(a.dev) * 5);
-    p.audioTaps = taps2.data();
-    p.audioTapCount = taps2.size();
-    p.audioDecimation = a.d2;
-    ConstRef<Filter> chain = unwrap(gsCreateFusedChain(&p, queue));
+    Ref<Filter> chainRef;
+    if (a.rftopcm.empty()) {
+      GsFusedChainParams p {};
+      p.structSize = sizeof(p);
+      p.inputType = SampleType_Int8Complex;
+      p.modulation = fm ? Modulation_Fm : Modulation_Am;
+      p.mix = 1;
+      p.sampleRate = a.fs;
+      p.frequency = a.freq;
+      p.rfTaps = taps1.data();
+      p.rfTapCount = taps1.size();
+      p.rfDecimation = a.d1;
+      p.fmGain = demodRate / (2.0f * static_cast<float>(M_PI) * static_cast<float>(a.dev) * 5);
+      p.audioTaps = taps2.data();
+      p.audioTapCount = taps2.size();
+      p.audioDecimation = a.d2;
+      chainRef = unwrap(gsCreateFusedChain(&p, queue));
+    } else {
+      // the reference's declarative route (applications/nbfm_test.cpp:546-562): a named queue, then the factory.
+      // channelFrequency - tunedFrequency = -freq, so the mixer runs at `freq` like the explicit chain above.
+      const double channel = a.tuned - a.freq;
+      if (a.rftopcm == "api") {  // complex-float input, the reference's own signature
+        chainRef = unwrap(factories->getRfToPcmAudioFactory()->createRfToPcm(
+            static_cast<float>(a.fs), fm ? Modulation_Fm : Modulation_Am, a.d1, a.d2, static_cast<float>(a.tuned), static_cast<float>(channel),
+            static_cast<float>(a.channelWidth), fm ? static_cast<float>(a.dev) : 0.0f, -60.0f, -60.0f, "q0"));
+      } else {
+        char json[1024];
+        snprintf(json, sizeof(json),
+                 "{\"rfSampleRate\": %.17g, \"modulation\": \"%s\", \"rfLowPassDecimation\": %zu, \"audioLowPassDecimation\": %zu, "
+                 "\"tunedFrequency\": %.17g, \"channelFrequency\": %.17g, \"channelWidth\": %.17g, \"fskDeviation\": %.17g, "
+                 "\"rfLowPassDbAttenuation\": -60, \"audioLowPassDbAttenuation\": -60, \"commandQueue\": \"q0\", \"inputType\": \"Int8Complex\"}",
+                 a.fs, fm ? "fm" : "am", a.d1, a.d2, a.tuned, channel, a.channelWidth, a.dev);
+        chainRef = unwrap(createFilter("RfToPcmAudio", json));
+      }
+    }
+    ConstRef<Filter> chain = chainRef;
     ConstRef<IAllocator> pinnedAlloc = unwrap(factories->getCudaAllocatorFactory()->createCudaAllocator(queue, 32, true));
     ConstRef<IBufferFactory> pinnedFactory = unwrap(factories->createBufferFactory(pinnedAlloc));
     ConstRef<IBuffer> host = unwrap(pinnedFactory->createBuffer(a.step * 4));
     vector<float> result;
     IBuffer* o[1];
     size_t total = 0;
+    vector<char> cf32;  // "api" mode: the same samples as complex floats (x / 128), 8 bytes per sample
+    if (a.rftopcm == "api") {
+      cf32.resize(input.size() * 4);
+      float* dst = reinterpret_cast<float*>(cf32.data());
+      for (size_t i = 0; i < input.size(); i++) dst[i] = static_cast<float>(static_cast<signed char>(input[i])) * (1.0f / 128.0f);
+    }
+    const vector<char>& stream = cf32.empty() ? input : cf32;
+    const size_t sampleBytes = cf32.empty() ? 2 : 8;
     const auto start = chrono::steady_clock::now();
     for (size_t rep = 0; rep < a.repeat; rep++) {
-      for (size_t pos = 0; pos < input.size();) {
-        const size_t step = input.size() - pos < a.step ? input.size() - pos : a.step;
+      for (size_t pos = 0; pos < stream.size();) {
+        size_t step = stream.size() - pos < a.step ? stream.size() - pos : a.step;
+        step -= step % sampleBytes;
         Ref<IBuffer> staged = request(h2d, 0, step);
-        memcpy(staged->writePtr(), input.data() + pos, step);
+        memcpy(staged->writePtr(), stream.data() + pos, step);
         THROW_IF_ERR(h2d->commitBuffer(0, step));
         pos += step;
-        total += step / 2;
+        total += step / sampleBytes;
         Ref<IBuffer> chainIn = request(chain, 0, h2d->getAlignedOutputDataSize(0));
         o[0] = chainIn.get();
         THROW_IF_ERR(h2d->readOutput(o, 1));

@@ -3,7 +3,7 @@
 # channelizer (strong scaling, channels).  gpurun --gpus 8 --timeout 900 -- 'bash tools/scale_run.sh'
 OUT=gpurun_out/scale
 mkdir -p $OUT
-for N in 1 2 4 8; do
+for N in ${NS:-1 2 4 8}; do
   for WL in am channelizer; do
     STEPS=$([ $WL = am ] && echo 200 || echo 20)
     if [ $N = 1 ]; then
