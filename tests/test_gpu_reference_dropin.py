@@ -105,3 +105,47 @@ def test_chain_through_reference_api(tmp_path, mod):
     assert abs(gold.size - ref.size) <= 1
     if mod == "am":
         assert rel_err(ref[:m], gold[:m]) < 5e-3
+
+
+@pytest.mark.parametrize("route", ["api", "json"])
+def test_rf_to_pcm_factory_demodulates_an_am_tone(tmp_path, route):
+    """SURVEY 8(f) rank 1: the declarative caller.  IRfToPcmAudioFactory::createRfToPcm (complex-float input, the reference's
+    signature: FilterFactories.h:159-175) and createFilter("RfToPcmAudio", json) with the additive int8 input both return ONE
+    fused Filter that designs its own taps; a carrier 1.234 MHz off the tuned frequency, amplitude-modulated by a 1 kHz
+    tone, must come out as that tone at 48 kHz, and the two routes must agree."""
+    exe = os.path.join(REF, "ref_chain_ours_hdr")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref chain drivers not built")
+    fs, off, d1, d2 = 19.2e6, 1.234e6, 40, 10
+    n = 1 << 22
+    t = np.arange(n) / fs
+    env = 60.0 * (1.0 + 0.5 * np.sin(2 * np.pi * 1e3 * t))
+    z = env * np.exp(2j * np.pi * off * t)
+    rng = np.random.default_rng(7)
+    x = np.empty(2 * n, dtype=np.int8)
+    x[0::2] = np.clip(np.rint(z.real + rng.normal(0, 2, n)), -127, 127)
+    x[1::2] = np.clip(np.rint(z.imag + rng.normal(0, 2, n)), -127, 127)
+    src = tmp_path / "in.i8"
+    x.tofile(src)
+
+    def run(which):
+        out = tmp_path / f"out_{which}.f32"
+        cmd = [exe, "--fs", repr(fs), "--freq", repr(-off), "--mod", "am", "--d1", str(d1), "--d2", str(d2), "--in", str(src), "--out", str(out),
+               "--rftopcm", which, "--tuned", "100e6", "--channel-width", "10e3", "--step", str(1 << 20)]
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
+        return np.fromfile(out, dtype=np.float32)
+
+    audio = run(route)
+    assert audio.size > 4000 and np.all(np.isfinite(audio))
+    seg = audio[1000:1000 + 4800].astype(np.float64)  # 0.1 s at 48 kHz, past the filters' start-up
+    spec = np.abs(np.fft.rfft((seg - seg.mean()) * np.hanning(seg.size)))
+    peak_hz = np.argmax(spec) * 48e3 / seg.size
+    assert abs(peak_hz - 1e3) <= 10.0, peak_hz
+    # envelope 60/128 * (1 +- 0.5) through unity-gain low-passes
+    assert abs(seg.mean() - 60.0 / 128.0) < 0.02 and abs((seg.max() - seg.min()) / 2 - 30.0 / 128.0) < 0.02
+    if route == "json":  # the int8 route (toepKernel) against the complex-float route (rows kernels): same taps, same stream
+        other = run("api")
+        m = min(audio.size, other.size)
+        assert abs(audio.size - other.size) <= 1
+        assert_close(audio[:m], other[:m], REL_TOL, "RfToPcmAudio json (int8) vs createRfToPcm (cf32)")
