@@ -317,7 +317,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
     }
   }
   if (c->toepPlan.ok) {
-    c->variant = toeplitzVariantName(c->toepPlan, c->D1, buf, sizeof(buf));
+    c->variant = toeplitzVariantName(c->toepPlan, buf, sizeof(buf));
   } else if (c->fusedPlan.fused) {
     c->variant = chainVariantName(c->elem, c->mix, c->fusedPlan, buf, sizeof(buf));
   } else {

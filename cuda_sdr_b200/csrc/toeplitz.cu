@@ -254,10 +254,9 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   return launchStatus();
 }
 
-const char* toeplitzVariantName(const ToepPlan& plan, unsigned D1, char* buf, size_t bufLen) {
+const char* toeplitzVariantName(const ToepPlan& plan, char* buf, size_t bufLen) {
   snprintf(buf, bufLen, "toeplitz<int8c,G=%u,%s>(kSteps=%u,warps=%u+%u,block=%u B,stages=%u,smem=%u,ctas/SM=%u,grid=%u)", plan.G,
            plan.magic ? "magic" : "i2f", plan.KS, plan.NW, plan.NA, plan.blockBytes, plan.S, plan.smemBytes, plan.ctasPerSm, plan.grid);
-  (void)D1;
   return buf;
 }
 

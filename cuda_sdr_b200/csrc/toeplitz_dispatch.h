@@ -26,6 +26,6 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
 void buildToeplitzFragments(const float* taps, unsigned T1, unsigned D1, bool mix, uint64_t phaseStep, double inScale, ToepPlan& plan,
                             std::vector<uint32_t>& frag, float digitScale[3]);
 cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t stream);
-const char* toeplitzVariantName(const ToepPlan& plan, unsigned D1, char* buf, size_t bufLen);
+const char* toeplitzVariantName(const ToepPlan& plan, char* buf, size_t bufLen);
 
 }  // namespace b200sdr
