@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "chain_dispatch.h"
+#include "digits.h"
 #include "chain_kernels.cuh"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
@@ -267,21 +268,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
       }
     }
     for (double v : B) bMax = std::fmax(bMax, std::fabs(v));
-    // three balanced digits in [-128, 127] reach 127*65536 + 127*256 + 127 = 8 355 711 on the positive side
-    const double scale = bMax > 0.0 ? 8355711.0 / bMax : 1.0;
-    c->digitScale[0] = static_cast<float>(1.0 / scale);
-    c->digitScale[1] = static_cast<float>(256.0 / scale);
-    c->digitScale[2] = static_cast<float>(65536.0 / scale);
+    const FixedPoint24 fx = fixedPoint24For(bMax);
+    for (int d = 0; d < 3; d++) c->digitScale[d] = fx.digitScale[d];
     std::vector<unsigned> frag(c->fusedPlan.bFragWords, 0u);
-    auto digits = [&](double v, int out[3]) {  // q = d2*65536 + d1*256 + d0 with every digit in [-128, 127]
-      long long q = std::llround(v * scale);
-      for (int d = 0; d < 3; d++) {
-        long long r = ((q % 256) + 256) % 256;
-        if (r >= 128) r -= 256;
-        out[d] = static_cast<int>(r);
-        q = (q - r) / 256;
-      }
-    };
     for (unsigned n8 = 0; n8 < NT; n8++)
       for (unsigned ks = 0; ks < KS; ks++)
         for (unsigned half = 0; half < 2; half++)
@@ -291,7 +280,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
             for (unsigned e = 0; e < 4; e++) {
               const unsigned k = ks * 32u + half * 16u + t * 4u + e, n = n8 * 8u + g;
               int dg[3];
-              digits(B[static_cast<size_t>(k) * N + n], dg);
+              balancedDigits(B[static_cast<size_t>(k) * N + n], fx.scale, dg);
               for (int d = 0; d < 3; d++) word[d] |= (static_cast<unsigned>(dg[d]) & 0xffu) << (8u * e);
             }
             for (unsigned d = 0; d < 3; d++) frag[(((d * NT + n8) * KS + ks) * 2u + half) * 32u + lane] = word[d];

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "channel_kernels.cuh"
+#include "digits.h"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
 #include "pfb_kernels.cuh"
@@ -140,10 +141,8 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
       }
     }
     for (double v : B) bMax = std::fmax(bMax, std::fabs(v));
-    const double scale = bMax > 0.0 ? 8355711.0 / bMax : 1.0;  // three balanced int8 digits reach +8 355 711
-    scales[ch * 3u] = static_cast<float>(1.0 / scale);
-    scales[ch * 3u + 1u] = static_cast<float>(256.0 / scale);
-    scales[ch * 3u + 2u] = static_cast<float>(65536.0 / scale);
+    const FixedPoint24 fx = fixedPoint24For(bMax);
+    for (unsigned d = 0; d < 3; d++) scales[ch * 3u + d] = fx.digitScale[d];
     for (unsigned m = 0; m < 8; m++) {
       double re, im;
       phasor(step * (static_cast<uint64_t>(m) * c->D1), re, im);
@@ -162,13 +161,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
             unsigned word[3] = {0, 0, 0};
             for (unsigned e = 0; e < 4; e++) {
               const unsigned k = ks * 32u + half * 16u + t * 4u + e, n = nt * 8u + g;
-              long long q = std::llround(B[static_cast<size_t>(k) * NCOL + n] * scale);
-              for (int d = 0; d < 3; d++) {
-                long long r = ((q % 256) + 256) % 256;
-                if (r >= 128) r -= 256;
-                word[d] |= (static_cast<unsigned>(r) & 0xffu) << (8u * e);
-                q = (q - r) / 256;
-              }
+              int dg[3];
+              balancedDigits(B[static_cast<size_t>(k) * NCOL + n], fx.scale, dg);
+              for (int d = 0; d < 3; d++) word[d] |= (static_cast<unsigned>(dg[d]) & 0xffu) << (8u * e);
             }
             const unsigned n = local * c->NTC + nt;
             for (unsigned d = 0; d < 3; d++)

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "digits.h"
 #include "toeplitz_dispatch.h"
 #include "toeplitz_kernels.cuh"
 
@@ -155,20 +156,8 @@ void buildToeplitzFragments(const float* taps, unsigned T1, unsigned D1, bool mi
       B[(byte + 1u) * 8u + 2u * n + 1u] = cr;
     }
   }
-  // three balanced digits in [-128, 127] reach 127*65536 + 127*256 + 127 = 8 355 711 on the positive side
-  const double scale = bMax > 0.0 ? 8355711.0 / bMax : 1.0;
-  digitScale[0] = static_cast<float>(1.0 / scale);
-  digitScale[1] = static_cast<float>(256.0 / scale);
-  digitScale[2] = static_cast<float>(65536.0 / scale);
-  auto digits = [&](double v, int out[3]) {  // q = d2*65536 + d1*256 + d0 with every digit in [-128, 127]
-    long long q = std::llround(v * scale);
-    for (int d = 0; d < 3; d++) {
-      long long r = ((q % 256) + 256) % 256;
-      if (r >= 128) r -= 256;
-      out[d] = static_cast<int>(r);
-      q = (q - r) / 256;
-    }
-  };
+  const FixedPoint24 fx = fixedPoint24For(bMax);
+  for (int d = 0; d < 3; d++) digitScale[d] = fx.digitScale[d];
   frag.assign(static_cast<size_t>(plan.Q) * 32u * 12u, 0u);
   double colAbs[3][8] = {};
   for (unsigned q = 0; q < plan.Q; q++)
@@ -180,7 +169,7 @@ void buildToeplitzFragments(const float* taps, unsigned T1, unsigned D1, bool mi
           for (unsigned e = 0; e < 4; e++) {
             const size_t byte = 32u * (2u * q + ksub) + 16u * half + 4u * t + e;
             int dg[3];
-            digits(B[byte * 8u + g], dg);
+            balancedDigits(B[byte * 8u + g], fx.scale, dg);
             for (int d = 0; d < 3; d++) {
               word[d] |= (static_cast<unsigned>(dg[d]) & 0xffu) << (8u * e);
               colAbs[d][g] += std::abs(dg[d]);
