@@ -25,6 +25,21 @@ namespace {
 
 size_t firCount(size_t nIn, size_t T, size_t D) { return (T == 0 || nIn + 1 < T) ? 0 : (nIn + 1 - T) / (D == 0 ? 1 : D); }
 
+// Do all frequencies equal f[0] + b * fs / 2^log2N for integers b?  Decided on the 64-bit phase steps the kernels mix with
+// (turns per sample, mod 1), with a slack of 2^-52 turns for their rounding; bins[ch] receives b mod 2^log2N.
+bool onRaster(const double* frequencies, unsigned count, double sampleRate, unsigned log2N, int* bins) {
+  const unsigned shift = 64u - log2N;
+  const uint64_t step0 = phaseStepOf(frequencies[0], sampleRate);
+  for (unsigned ch = 0; ch < count; ch++) {
+    const uint64_t d = phaseStepOf(frequencies[ch], sampleRate) - step0;  // wraps: turns are mod 1
+    const uint64_t b = (d + (1ull << (shift - 1))) >> shift;              // nearest bin
+    const int64_t resid = static_cast<int64_t>(d - (b << shift));
+    if (resid < -4096 || resid > 4096) return false;
+    if (bins) bins[ch] = static_cast<int>(b & ((1ull << log2N) - 1ull));
+  }
+  return true;
+}
+
 b200sdr_status cudaFailC(cudaError_t e, const char* where) {
   return chainFail(e == cudaErrorMemoryAllocation ? B200SDR_OUT_OF_MEMORY : B200SDR_RUNTIME_ERROR, std::string(where) + ": " + cudaGetErrorString(e));
 }
@@ -74,6 +89,13 @@ B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
 }
 
 B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer* c) { return c ? c->variant.c_str() : ""; }
+
+B200SDR_EXPORT uint32_t b200sdr_channelizer_raster(const double* frequencies, uint32_t numChannels, double sampleRate, int32_t* bins) {
+  if (!frequencies || numChannels == 0 || !(sampleRate > 0.0)) return 0;
+  for (unsigned log2N = 2; log2N <= 8; log2N++)
+    if (onRaster(frequencies, numChannels, sampleRate, log2N, bins)) return 1u << log2N;
+  return 0;
+}
 
 B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channelizer_config* cfg, b200sdr_channelizer** out) {
   if (!cfg || !out) return chainFail(B200SDR_INVALID_ARGUMENT, "config and out must be non-null");
@@ -178,18 +200,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   {
     const char* e = std::getenv("B200SDR_PFB");
     const bool allowed = !(e && std::atoi(e) == 0) && c->C <= kPfbMaxN && c->D1 % 2u == 0;
-    const uint64_t step0 = phaseStepOf(cfg->frequencies[0], cfg->sample_rate);
+    const uint64_t step0 = phaseStepOf(cfg->frequencies[0], cfg->sample_rate);  // the common offset goes into the taps
     for (unsigned log2N = 2; allowed && !c->pfb && log2N <= 8; log2N++) {
-      const unsigned shift = 64u - log2N;
-      bool fits = true;
-      for (unsigned ch = 0; ch < c->C && fits; ch++) {
-        const uint64_t d = phaseStepOf(cfg->frequencies[ch], cfg->sample_rate) - step0;  // wraps: turns are mod 1
-        const uint64_t b = (d + (1ull << (shift - 1))) >> shift;                          // nearest bin (mod N)
-        const int64_t resid = static_cast<int64_t>(d - (b << shift));
-        fits = resid >= -4096 && resid <= 4096;  // 2^-52 turns: the frequencies were rounded to 2^-64 turns per sample
-        pfbBin[ch] = static_cast<int>(b & ((1ull << log2N) - 1ull));
-      }
-      if (!fits) continue;
+      if (!onRaster(cfg->frequencies, c->C, cfg->sample_rate, log2N, pfbBin.data())) continue;
       const unsigned N = 1u << log2N, Qn = (c->T1 + N - 1u) / N;
       const PfbSmem lay = pfbSmemLayout(N, Qn, c->D1, c->C);
       if (lay.total > 226u * 1024u) continue;  // a finer raster has fewer taps per phase: keep looking

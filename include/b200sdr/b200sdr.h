@@ -159,6 +159,11 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
     b200sdr_channelizer* channelizer, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
     size_t audioStride, size_t numAudio, cudaStream_t stream);
 B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer* channelizer);
+/* The coarsest raster the channel set lies on: the smallest N in {4, 8, ..., 256} with frequencies[c] = frequencies[0] +
+   b_c * sampleRate / N (decided on the 64-bit phase steps, i.e. mod sampleRate), or 0 if there is none.  bins (may be NULL)
+   receives b_c mod N.  A non-zero answer is what sends b200sdr_channelizer_create down the filter-bank route (which may
+   still pick a finer raster if the tables of the coarsest do not fit in shared memory).  Needs no GPU. */
+B200SDR_EXPORT uint32_t b200sdr_channelizer_raster(const double* frequencies, uint32_t numChannels, double sampleRate, int32_t* bins);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* Kernels launched by this library since load (all streams); used by bench.py's gpu_launches. */
