@@ -88,6 +88,7 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
         const unsigned OTW = 64u * G - fm, OT = warps * OTW;
         const unsigned span = (T2 - 1u + OT - 1u) / OT;  // tiles an audio window reaches back
         if (span > kToepLines - 2u) continue;
+        if (((T2 + 3u) & ~3u) > OT) continue;  // keep the mirror inside the first tile of the ring (longer audio filters: other routes)
         const ToepSmem lay = toepSmemLayout(p.Q, T2, OT, warps, stages, slotBytes);
         if (lay.total > kSmemPerSm - kSmemPerCtaReserve) continue;
         unsigned ctas = kSmemPerSm / (lay.total + kSmemPerCtaReserve);

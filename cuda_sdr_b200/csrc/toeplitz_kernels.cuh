@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
         const unsigned o = j * 64u + h * 32u + lane;
         if (o < OTW) {
           dst[o] = dmv[j][h];
-          if (line == 0 && warp * OTW + o < mirror) ring[R + warp * OTW + o] = dmv[j][h];  // windows that cross the end of the ring
+          const unsigned idx = line * OT + warp * OTW + o;      // position in the ring
+          if (idx < mirror) ring[R + idx] = dmv[j][h];          // windows that cross the end of the ring read on here
         }
       }
     __syncwarp();

@@ -175,7 +175,7 @@ def test_two_kernel_path_segments_concatenate_bit_exactly(sdr, monkeypatch):
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_MMA": "0", "B200SDR_CHAIN_RPT": "1"},
     {"B200SDR_FUSED": "1", "B200SDR_CHAIN_STAGES": "3", "B200SDR_CHAIN_RPT": "2"},
     {"B200SDR_TOEPLITZ": "1"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_G": "1"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_STAGES": "3"},
-    {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "2"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "8", "B200SDR_TOEP_G": "1"},
+    {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "3"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "8", "B200SDR_TOEP_G": "1"},
     {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_MAGIC": "0"}, {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_WARPS": "6", "B200SDR_TOEP_G": "1"},
     {"B200SDR_TOEPLITZ": "1", "B200SDR_TOEP_CTAS": "1", "B200SDR_TOEP_WARPS": "3"},
 ])
