@@ -211,6 +211,9 @@ def run_reference_arm(args):
     import numpy as np
     from oracle import oracle as orc
 
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would leave the
+    # reference arm on one core at N > 1
+    orc.set_num_threads(len(os.sched_getaffinity(0)))
     spec = orc.ChainSpec(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], wl["gain"], wl["t2"], wl["d2"])
     # bounded sample per step so that steps+warmup finish within minutes on any host
     rng = np.random.default_rng(0x5D120001)
