@@ -87,6 +87,8 @@ B200SDR_SYMBOLS = {
     "b200sdr_channelizer_destroy": (None, [vp]),
     "b200sdr_channelizer_counts": (None, [vp, sz, psz, psz]),
     "b200sdr_channelizer_run": (u32, [vp, vp, sz, vp, sz, vp, sz, sz, stream_t]),
+    "b200sdr_channelizer_channel_counts": (u32, [vp, u32, sz, psz, psz]),
+    "b200sdr_channelizer_process": (u32, [vp, vp, sz, vp, sz, vp, sz, psz, stream_t]),
     "b200sdr_channelizer_variant": (C.c_char_p, [vp]),
     "b200sdr_channelizer_raster": (u32, [C.POINTER(f64), u32, f64, C.POINTER(i32)]),
     "b200sdr_launch_count": (u64, []),

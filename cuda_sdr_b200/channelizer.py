@@ -63,6 +63,29 @@ class Channelizer:
         _lib.b200sdr_channelizer_counts(self._h, n_in, C.byref(demod), C.byref(audio))
         return demod.value, audio.value
 
+    def channel_counts(self, channel: int, n_in: int):
+        """(demod, audio) counts of one channel by the reference's per-node rules (an AM channel keeps its own count)."""
+        demod, audio = C.c_size_t(), C.c_size_t()
+        N.check_status(_lib.b200sdr_channelizer_channel_counts(self._h, channel, n_in, C.byref(demod), C.byref(audio)),
+                       "b200sdr_channelizer_channel_counts")
+        return demod.value, audio.value
+
+    def process(self, x: torch.Tensor, out: torch.Tensor | None = None, scratch: torch.Tensor | None = None):
+        """One block by the reference's count rules.  Returns (audio[num_channels, max count], counts[num_channels])."""
+        assert x.is_cuda and x.dtype == torch.int8 and x.is_contiguous()
+        n_in = x.numel() // 2
+        n_max = max(self.channel_counts(c, n_in)[1] for c in range(self.num_channels))
+        n_demod = max((n_max - 1) * self.D2 + self.T2 if n_max else 0, self.T2)
+        if out is None:
+            out = torch.zeros(self.num_channels, max(n_max, 1), dtype=torch.float32, device=x.device)
+        if scratch is None:
+            scratch = torch.empty(self.num_channels, max(n_demod, 1), dtype=torch.float32, device=x.device)
+        counts = (C.c_size_t * self.num_channels)()
+        st = _lib.b200sdr_channelizer_process(self._h, x.data_ptr(), n_in, scratch.data_ptr(), scratch.stride(0), out.data_ptr(), out.stride(0),
+                                              counts, torch.cuda.current_stream(x.device).cuda_stream)
+        N.check_status(st, "b200sdr_channelizer_process")
+        return out[:, :n_max], [int(v) for v in counts]
+
     def run(self, x: torch.Tensor, n_audio: int | None = None, out: torch.Tensor | None = None,
             scratch: torch.Tensor | None = None) -> torch.Tensor:
         """x: device int8 IQ (2 * n_in bytes).  Returns audio[num_channels, n_audio] (device)."""

@@ -35,6 +35,7 @@ struct ChannelParams {
   unsigned long long outStride;
   unsigned D1, M, kSteps;
   unsigned numChannels;
+  int forceAm;               // demodulate every channel as AM whatever `mod` says (the AM tail pass of a mixed AM/FM set)
 };
 
 constexpr int kChanNC = 4;        // channels per CTA
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) channelKernel(const ChannelParams prm) {
         y1.y += v1.y;
       }
       float o;
-      if (prm.mod[ch] == 1) {  // FM: gain * arg(y[k+1] * conj(y[k]) * exp(j*w*D1))
+      if (prm.mod[ch] == 1 && !prm.forceAm) {  // FM: gain * arg(y[k+1] * conj(y[k]) * exp(j*w*D1))
         const float2 d = make_float2(fmaf(y1.y, y.y, y1.x * y.x), fmaf(y1.y, y.x, -y1.x * y.y));
         const float2 r1 = prm.rot[ch * 8u + 1u];
         o = prm.gain[ch] * atan2f(fmaf(d.y, r1.x, d.x * r1.y), fmaf(-d.y, r1.y, d.x * r1.x));

@@ -49,7 +49,8 @@ b200sdr_status cudaFailC(cudaError_t e, const char* where) {
 struct b200sdr_channelizer {
   int device = 0;
   unsigned C = 0, T1 = 0, D1 = 1, M = 0, NTC = 1, KS = 0, T2 = 0, D2 = 1, groups = 0, warps = 4;
-  bool anyFm = false;
+  bool anyFm = false, anyAm = false;
+  float* dTail = nullptr;  // [C]: the AM channels' extra last output of a mixed AM/FM set (b200sdr_channelizer_process)
   unsigned* dBFrag = nullptr;
   float2* dRot = nullptr;
   float* dScale = nullptr;
@@ -66,12 +67,14 @@ struct b200sdr_channelizer {
   int* dPfbBin = nullptr;
   int* dPfbOrder = nullptr;
   float2* dPfbRot1 = nullptr;
+  std::vector<int> hostMods;
   std::string variant;
 };
 
 B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
   if (!c) return;
   DeviceGuard guard(c->device);
+  cudaFree(c->dTail);
   cudaFree(c->dBFrag);
   cudaFree(c->dRot);
   cudaFree(c->dScale);
@@ -172,6 +175,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
     }
     mods[ch] = cfg->modulations[ch] == B200SDR_MOD_FM ? 1 : 0;
     c->anyFm = c->anyFm || mods[ch] == 1;
+    c->anyAm = c->anyAm || mods[ch] == 0;
     gains[ch] = mods[ch] == 1 ? cfg->fm_gains[ch] : 1.0f;
 
     const unsigned group = ch / kChanNC, local = ch % kChanNC;
@@ -255,6 +259,13 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
        upload(gains.data(), gains.size() * sizeof(float), reinterpret_cast<void**>(&c->dGain)) &&
        upload(mods.data(), mods.size() * sizeof(int), reinterpret_cast<void**>(&c->dMod)) &&
        upload(cfg->audio_taps, sizeof(float) * c->T2, reinterpret_cast<void**>(&c->dTaps2));
+  if (ok && c->anyFm && c->anyAm) {
+    const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dTail), sizeof(float) * c->C);
+    if (e != cudaSuccess) {
+      st = cudaFailC(e, "cudaMalloc");
+      ok = false;
+    }
+  }
   if (ok && c->pfb) {
     std::vector<int> pfbOrder;  // AM channels first, then FM: a warp demodulates 32 channels of one kind per instruction
     for (int kind = 0; kind < 2; kind++)
@@ -284,6 +295,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
     snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched audio FIR", c->pfbN, c->C,
              c->pfbQn, kPfbTileK, kPfbWarps, c->pfbSmem);
   c->variant = buf;
+  c->hostMods = mods;
   *out = c;
   return B200SDR_OK;
 }
@@ -301,9 +313,66 @@ B200SDR_EXPORT void b200sdr_channelizer_counts(const b200sdr_channelizer* c, siz
   if (numAudio) *numAudio = audio;
 }
 
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_channel_counts(
+    const b200sdr_channelizer* c, uint32_t channel, size_t numInputs, size_t* numDemod, size_t* numAudio) {
+  if (numDemod) *numDemod = 0;
+  if (numAudio) *numAudio = 0;
+  if (!c || channel >= c->C) return chainFail(B200SDR_INVALID_ARGUMENT, "channel out of range");
+  const size_t rf = firCount(numInputs, c->T1, c->D1);
+  const size_t demod = c->hostMods[channel] == 1 ? (rf == 0 ? 0 : rf - 1) : rf;  // QuadFmDemod.cpp:76-84 keeps one sample
+  if (numDemod) *numDemod = demod;
+  if (numAudio) *numAudio = firCount(demod, c->T2, c->D2);
+  return B200SDR_OK;
+}
+
+namespace {
+
+// the AM channels' rows of tail[] -> column `col` of audio (one thread per channel)
+__global__ void scatterAmTail(const float* tail, const int* mod, float* audio, size_t audioStride, size_t col, unsigned channels) {
+  const unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch < channels && mod[ch] == 0) audio[static_cast<size_t>(ch) * audioStride + col] = tail[ch];
+}
+
+b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
+                       size_t audioStride, size_t numAudio, bool forceAm, cudaStream_t stream);
+
+}  // namespace
+
 B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
     b200sdr_channelizer* c, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio, size_t audioStride,
     size_t numAudio, cudaStream_t stream) {
+  return runImpl(c, input, numInputs, demodScratch, demodStride, audio, audioStride, numAudio, false, stream);
+}
+
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_process(
+    b200sdr_channelizer* c, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio, size_t audioStride,
+    size_t* numAudioPerChannel, cudaStream_t stream) {
+  if (!c) return chainFail(B200SDR_INVALID_ARGUMENT, "channelizer is null");
+  size_t common = 0;
+  b200sdr_channelizer_counts(c, numInputs, nullptr, &common);
+  const size_t rf = firCount(numInputs, c->T1, c->D1);
+  const size_t amAudio = firCount(rf, c->T2, c->D2);  // an AM channel's own count; the FM count is `common` when FM channels exist
+  if (numAudioPerChannel)
+    for (unsigned ch = 0; ch < c->C; ch++) numAudioPerChannel[ch] = c->hostMods[ch] == 1 ? common : amAudio;
+  b200sdr_status st = runImpl(c, input, numInputs, demodScratch, demodStride, audio, audioStride, common, false, stream);
+  if (st != B200SDR_OK || !(c->anyFm && c->anyAm) || amAudio == common) return st;
+  // Mixed set and the AM channels own one more output than the FM ones (their demodulator holds no sample back): the AM
+  // pass over the input window of that last output alone, every channel demodulated as AM, AM rows scattered into place.
+  if (audioStride < amAudio || demodStride < c->T2) return chainFail(B200SDR_INVALID_ARGUMENT, "demodStride/audioStride too small for the AM channels");
+  const size_t first = (amAudio - 1) * static_cast<size_t>(c->D1) * c->D2;  // a multiple of 8 samples: the slice stays 16-byte aligned
+  st = runImpl(c, static_cast<const unsigned char*>(input) + 2 * first, numInputs - first, demodScratch, demodStride, c->dTail, 1, 1, true, stream);
+  if (st != B200SDR_OK) return st;
+  DeviceGuard guard(c->device);
+  scatterAmTail<<<(c->C + 127u) / 128u, 128, 0, stream>>>(c->dTail, c->dMod, audio, audioStride, amAudio - 1, c->C);
+  const cudaError_t e = launchStatus();
+  if (e != cudaSuccess) return cudaFailC(e, "scatterAmTail launch");
+  return B200SDR_OK;
+}
+
+namespace {
+
+b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
+                       size_t audioStride, size_t numAudio, bool forceAm, cudaStream_t stream) {
   if (!c) return chainFail(B200SDR_INVALID_ARGUMENT, "channelizer is null");
   if (numAudio == 0) return B200SDR_OK;
   if (!input || !demodScratch || !audio) return chainFail(B200SDR_INVALID_ARGUMENT, "input/demodScratch/audio is null");
@@ -313,7 +382,8 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   // demod output k reads rows k .. k+M (FM: one more RF output), i.e. input up to (k + 1) * D1 + T1 - 1 at most
   const size_t needed = (nDemod - 1 + 1) * static_cast<size_t>(c->D1) + c->T1;
   const size_t neededAm = (nDemod - 1) * static_cast<size_t>(c->D1) + c->T1;
-  if (numInputs < (c->anyFm ? needed : neededAm)) return chainFail(B200SDR_OUT_OF_RANGE, "numAudio outputs need more input samples than numInputs");
+  const bool anyFm = c->anyFm && !forceAm;
+  if (numInputs < (anyFm ? needed : neededAm)) return chainFail(B200SDR_OUT_OF_RANGE, "numAudio outputs need more input samples than numInputs");
   DeviceGuard guard(c->device);
   if (guard.status != cudaSuccess) return cudaFailC(guard.status, "cudaSetDevice");
 
@@ -338,12 +408,13 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
     pp.N = c->pfbN;
     pp.Qn = c->pfbQn;
     pp.C = c->C;
-    pp.anyFm = c->anyFm ? 1 : 0;
+    pp.anyFm = anyFm ? 1 : 0;
+    pp.forceAm = forceAm ? 1 : 0;
     e = cudaFuncSetAttribute(reinterpret_cast<const void*>(pfbKernel), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaFailC(e, "cudaFuncSetAttribute");
     int sms = kSmCount;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const unsigned tileOut = kPfbTileK - (c->anyFm ? 1u : 0u);
+    const unsigned tileOut = kPfbTileK - (anyFm ? 1u : 0u);
     const unsigned long long pfbTiles = (nDemod + tileOut - 1) / tileOut;
     const unsigned grid = pfbTiles < static_cast<unsigned long long>(sms) ? static_cast<unsigned>(pfbTiles) : static_cast<unsigned>(sms);
     pfbKernel<<<grid, kPfbWarps * 32u, c->pfbSmem, stream>>>(pp);
@@ -365,6 +436,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   prm.M = c->M;
   prm.kSteps = c->KS;
   prm.numChannels = c->C;
+  prm.forceAm = forceAm ? 1 : 0;
   const unsigned rowsTile = c->warps * 32u, OT = rowsTile - c->M;
   const unsigned NT = kChanNC * c->NTC;
   const size_t ring = static_cast<size_t>(kChanStages) * (static_cast<size_t>(rowsTile) * kChanARow + static_cast<size_t>(NT) * 3u * 64u * 4u);
@@ -406,3 +478,5 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
   if (e != cudaSuccess) return cudaFailC(e, "batched audio FIR launch");
   return B200SDR_OK;
 }
+
+}  // namespace

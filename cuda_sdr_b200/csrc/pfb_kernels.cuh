@@ -53,6 +53,7 @@ struct PfbParams {
   unsigned long long outStride;
   unsigned D1, N, Qn, C;
   int anyFm;
+  int forceAm;                  // demodulate every channel as AM whatever `mod` says (the AM tail pass of a mixed AM/FM set)
 };
 
 struct PfbSmem {
@@ -148,7 +149,7 @@ __device__ __forceinline__ double pfbSample(unsigned w) {
 __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams prm) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned N = prm.N, Qn = prm.Qn, D = prm.D1, C = prm.C;
-  const bool fm = prm.anyFm != 0;
+  const bool fm = prm.anyFm != 0 && prm.forceAm == 0;
   const PfbSmem lay = pfbSmemLayout(N, Qn, D, C);
   double* tapsRe = reinterpret_cast<double*>(smem + lay.tapsReOff);
   double* tapsIm = reinterpret_cast<double*>(smem + lay.tapsImOff);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams p
     const int ch = i < C ? prm.order[i] : -1;
     chL[slot] = ch;
     binL[slot] = ch >= 0 ? prm.bin[ch] : 0;
-    modL[slot] = ch >= 0 ? prm.mod[ch] : 0;
+    modL[slot] = ch >= 0 && prm.forceAm == 0 ? prm.mod[ch] : 0;
     gainL[slot] = ch >= 0 ? prm.gain[ch] : 0.0f;
     rotL[slot] = ch >= 0 ? prm.rot1[ch] : make_float2(1.0f, 0.0f);
   }

@@ -124,6 +124,10 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
           p.smemBytes = lay.total;
           p.ctasPerSm = ctas;
           p.grid = static_cast<unsigned>(sms) * ctas;
+          // B200SDR_TOEP_GRID: fewer CTAs than the machine holds, so that each one walks many tiles (parity tests use it to
+          // wrap the demod ring several times on small inputs)
+          const int forcedGrid = envInt("B200SDR_TOEP_GRID", 0);
+          if (forcedGrid > 0 && static_cast<unsigned>(forcedGrid) < p.grid) p.grid = static_cast<unsigned>(forcedGrid);
         }
         if (total >= 8u) return p;
       }

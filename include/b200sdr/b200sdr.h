@@ -150,7 +150,8 @@ typedef struct b200sdr_channelizer b200sdr_channelizer;
 
 B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channelizer_config* config, b200sdr_channelizer** out);
 B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* channelizer);
-/* Per-channel output counts for numInputs input samples, by the reference's count rules (as b200sdr_chain_counts). */
+/* Output counts COMMON to all channels for numInputs input samples (the reference's count rules, as b200sdr_chain_counts;
+ * with FM channels in the set this is the FM count -- see b200sdr_channelizer_channel_counts for a channel's own). */
 B200SDR_EXPORT void b200sdr_channelizer_counts(const b200sdr_channelizer* channelizer, size_t numInputs, size_t* numDemod, size_t* numAudio);
 /* input: DEVICE int8 IQ (16-byte aligned); demodScratch: DEVICE, num_channels * demodStride floats with
  * demodStride >= numDemod needed for numAudio outputs ((numAudio-1)*D2 + T2); audio: DEVICE, [channel][audioStride].
@@ -158,6 +159,19 @@ B200SDR_EXPORT void b200sdr_channelizer_counts(const b200sdr_channelizer* channe
 B200SDR_EXPORT b200sdr_status b200sdr_channelizer_run(
     b200sdr_channelizer* channelizer, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
     size_t audioStride, size_t numAudio, cudaStream_t stream);
+/* Output counts of ONE channel by the reference's per-node rules (Fir.cpp:141-187; QuadFmDemod.cpp:76-84 holds one sample
+ * back, QuadAmDemod.cpp:80-107 none): an AM channel next to FM channels owns its single-chain count, which may be one audio
+ * sample more than b200sdr_channelizer_counts (the count common to all channels) reports. */
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_channel_counts(
+    const b200sdr_channelizer* channelizer, uint32_t channel, size_t numInputs, size_t* numDemod, size_t* numAudio);
+/* One block by the reference's count rules, channel by channel: as b200sdr_channelizer_run with the common count, plus --
+ * when the set mixes AM and FM and the AM channels own one more output -- an AM pass over the input window of that last
+ * output.  numAudioPerChannel (HOST, num_channels entries, may be NULL) receives each channel's count = what
+ * b200sdr_channelizer_channel_counts reports.  audioStride must hold the largest count, demodStride >= max(numDemod needed,
+ * audio_tap_count). */
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_process(
+    b200sdr_channelizer* channelizer, const void* input, size_t numInputs, float* demodScratch, size_t demodStride, float* audio,
+    size_t audioStride, size_t* numAudioPerChannel, cudaStream_t stream);
 B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer* channelizer);
 /* The coarsest raster the channel set lies on: the smallest N in {4, 8, ..., 256} with frequencies[c] = frequencies[0] +
    b_c * sampleRate / N (decided on the 64-bit phase steps, i.e. mod sampleRate), or 0 if there is none.  bins (may be NULL)

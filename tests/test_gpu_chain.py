@@ -236,3 +236,61 @@ def test_c2_full_size_properties(sdr):
         ref, _, _ = orc.chain(spec, xs, n0=i0)
         m = min(ref.size, 64)
         assert_close(out[a0:a0 + m].cpu().numpy(), ref[:m], what=f"window@{a0}")
+
+
+@pytest.mark.parametrize("env", [
+    {"B200SDR_TOEP_GRID": "1"}, {"B200SDR_TOEP_GRID": "3"}, {"B200SDR_TOEP_GRID": "7"},
+    {"B200SDR_TOEP_GRID": "2", "B200SDR_TOEP_G": "1"}, {"B200SDR_TOEP_GRID": "5", "B200SDR_TOEP_WARPS": "3"},
+    {"B200SDR_TOEP_GRID": "2", "B200SDR_TOEP_AUDIO_WARPS": "1"}, {"B200SDR_TOEP_GRID": "4", "B200SDR_TOEP_AUDIO_WARPS": "3"},
+    {"B200SDR_TOEP_GRID": "3", "B200SDR_TOEP_STAGES": "3"},
+])
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_demod_ring_wraps_many_times(sdr, monkeypatch, env, which):
+    """toepKernel's demod ring holds 4 tiles and wraps only when a CTA walks more than that.  With the grid limited to a
+    few CTAs every CTA runs >= 9 tiles on a 2^22-sample input, so the ring (and its mirror past the end) wraps at least
+    twice: AM with even D2 = 10 (paired loads) and FM with OTW = 64G - 1, odd D2 = 5 (scalar loads), the shape the bench
+    runs for C3."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    kw = c2_spec(sdr) if which == "c2" else c3_spec(sdr)
+    n = (1 << 22) + 4321
+    x = sdr.synth.int8_iq(n, seed=23)
+    chain, _ = check_chain(sdr, kw, x, n0=777, what=f"{which} {env}")
+    assert chain.variant.startswith("toeplitz<"), chain.variant
+    grid = int(env["B200SDR_TOEP_GRID"])
+    assert f"grid={grid})" in chain.variant, chain.variant
+    # tiles per CTA: demod samples / (warps * (64 G - fm)) / grid
+    import re
+    m = re.search(r"G=(\d).*warps=(\d+)\+", chain.variant)
+    ot = int(m.group(2)) * (64 * int(m.group(1)) - (1 if which == "c3" else 0))
+    assert chain.counts(n)[1] / ot / grid >= 9.0
+
+
+def test_c3_full_size_properties(sdr):
+    """BASELINE size for the WBFM chain (2^28 int8 IQ samples, the shape `bench.py --workload wbfm` times): exact output
+    count, finiteness, and random windows of the full-size result against the oracle run on just the input slice each
+    window depends on.  Every CTA walks ~44 tiles here, so the FM demod ring wraps ~11 times."""
+    kw = c3_spec(sdr)
+    chain = sdr.Chain(**kw)
+    assert chain.variant.startswith("toeplitz<"), chain.variant
+    n = 1 << 28
+    x = sdr.synth.device_int8_iq(n, DEV)
+    out = chain.process_device(x)
+    assert out.numel() == orc.chain_num_outputs(n, 545, 80, 1, 273, 5) == chain.counts(n)[2]
+    assert bool(torch.isfinite(out).all())
+    spec = oracle_spec(kw)
+    rng = np.random.default_rng(2)
+    for a0 in [0, out.numel() - 64] + list(rng.integers(0, out.numel() - 64, size=6)):
+        a0 = int(a0)
+        i0 = a0 * chain.stride
+        icnt = 63 * chain.stride + chain.window + chain.stride + chain.rf_decim
+        icnt = min(icnt, n - i0)
+        xs = x[2 * i0: 2 * (i0 + icnt)].cpu().numpy()
+        ref, _, _ = orc.chain(spec, xs, n0=i0)
+        m = min(ref.size, 64)
+        assert_close(out[a0:a0 + m].cpu().numpy(), ref[:m], tol=2e-5, what=f"window@{a0}")
+    # segments of the full-size block concatenate bit-exactly (the multi-GPU decomposition at bench size)
+    n_audio = out.numel()
+    a0, cnt, i0, icnt = chain.segment(n_audio, 8, 5)
+    part = chain.run(x[2 * i0: 2 * (i0 + icnt)], cnt, i0, n_in=icnt)
+    assert torch.equal(part.view(torch.int32), out[a0:a0 + cnt].view(torch.int32))

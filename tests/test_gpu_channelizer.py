@@ -27,18 +27,19 @@ def make(sdr, fs, freqs, mods, T1, D1, T2, D2, dev_hz):
 def check(sdr, fs, freqs, mods, T1, D1, T2, D2, n, dev_hz=5e3, seed=3):
     ch, t1, t2, gains = make(sdr, fs, freqs, mods, T1, D1, T2, D2, dev_hz)
     x = sdr.synth.int8_iq(n, seed=seed, sample_rate=fs)
-    got = ch.run(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    out, counts = ch.process(torch.from_numpy(x).to(DEV))
+    got = out.cpu().numpy()
     n_demod, n_audio = ch.counts(n)
-    assert got.shape == (len(freqs), n_audio)
+    assert min(counts) == n_audio and got.shape == (len(freqs), max(counts))
     for c, (f, m) in enumerate(zip(freqs, mods)):
         spec = orc.ChainSpec(fs, f, t1, D1, m, gains[c], t2, D2)
         ref, _, _ = orc.chain(spec, x)
-        # with FM channels present every channel uses the FM count (one RF output held back): an AM channel may be one
-        # audio sample short of its own single-chain count, never more
-        assert n_audio <= ref.size <= n_audio + 1
+        # counts are exact PER CHANNEL: an AM channel next to FM channels emits its own single-chain count (Fir.cpp:181-186
+        # applied to that channel's demodulator output), not the FM channels' count
+        assert counts[c] == ref.size == ch.channel_counts(c, n)[1], (c, m, counts[c], ref.size)
         tol = 2e-5 if m == 1 else 1e-5
-        assert_close(got[c], ref[:n_audio], tol=tol, what=f"channel {c} ({'FM' if m else 'AM'}, f={f})")
-    return ch, got
+        assert_close(got[c, :counts[c]], ref, tol=tol, what=f"channel {c} ({'FM' if m else 'AM'}, f={f})")
+    return ch, got[:, :n_audio]
 
 
 def test_small_mixed_channels(sdr):
@@ -60,6 +61,24 @@ def test_c5_shape_eight_channels(sdr):
     freqs = [(-4 + i) * 600e3 + 37e3 for i in range(8)]
     mods = [i & 1 for i in range(8)]
     check(sdr, fs, freqs, mods, T1=4097, D1=640, T2=273, D2=5, n=(1 << 21) + 777, dev_hz=75e3)
+
+
+@pytest.mark.parametrize("pfb", ["1", "0"])
+def test_am_channels_keep_their_own_count_next_to_fm(sdr, monkeypatch, pfb):
+    """Input lengths swept over one audio-decimation period of RF outputs: for exactly one residue the AM channels own one
+    more audio sample than the FM channels (the FM discriminator holds one RF output back); both routes must emit it."""
+    monkeypatch.setenv("B200SDR_PFB", pfb)
+    fs, T1, D1, T2, D2 = 1.024e6, 400, 64, 33, 5
+    freqs = [7e3 + b * fs / 16 for b in (0, 3, 5, 15, 9)]
+    mods = [0, 1, 0, 1, 1]
+    differ = 0
+    for extra_rf in range(D2):
+        n = T1 - 1 + D1 * (2000 + extra_rf) + 17
+        ch, _ = check(sdr, fs, freqs, mods, T1, D1, T2, D2, n=n, seed=40 + extra_rf)
+        am, fm_ = ch.channel_counts(0, n)[1], ch.channel_counts(1, n)[1]
+        assert am - fm_ in (0, 1)
+        differ += am - fm_
+    assert differ == 1
 
 
 def test_counts_and_short_inputs(sdr):
@@ -154,3 +173,36 @@ def test_filter_bank_time_segments_concatenate_bit_exactly(sdr):
         cat = torch.cat(cols, dim=1)
         assert cat.shape == whole.shape
         assert torch.equal(cat.view(torch.int32), whole.view(torch.int32)), parts
+
+
+# ---- the BASELINE C5 shape at its full channel count ----------------------------------------------------------------------
+_C5_CACHE = {}
+
+
+@pytest.mark.parametrize("pfb", ["1", "0"])
+def test_c5_256_channels_against_the_oracle(sdr, monkeypatch, pfb):
+    """BASELINE configs[4] as the bench runs it: 256 channels on the 600 kHz raster alternating AM/FM, 4097 taps / 640, 273
+    audio taps / 5, on 2^24 samples -- EVERY channel of both routes (filter bank with N = 256 fully populated; per-channel
+    int8 GEMM) against the fp64 oracle run channel by channel, with per-channel exact counts."""
+    monkeypatch.setenv("B200SDR_PFB", pfb)
+    fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5
+    total = 256
+    freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]
+    mods = [c & 1 for c in range(total)]
+    t1 = sdr.taps.lowpass(T1, 100e3, fs)
+    t2 = sdr.taps.lowpass(T2, 0.45 * 48e3, fs / D1)
+    gain = sdr.fm_gain(fs / D1, 75e3)
+    ch = sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=[gain] * total)
+    assert ch.variant.startswith("pfb<N=256,fp64>" if pfb == "1" else "channel<imma"), ch.variant
+    n = (1 << 24) + 640 * 3 + 11
+    if "x" not in _C5_CACHE:  # the input and the 256 oracle runs are shared by the two routes
+        _C5_CACHE["x"] = sdr.synth.int8_iq(n, seed=0x5D120005 & 0xffff, sample_rate=fs)
+        _C5_CACHE["ref"] = [orc.chain(orc.ChainSpec(fs, freqs[c], t1, D1, mods[c], gain, t2, D2), _C5_CACHE["x"])[0] for c in range(total)]
+    x = _C5_CACHE["x"]
+    out, counts = ch.process(torch.from_numpy(x).to(DEV))
+    got = out.cpu().numpy()
+    for c in range(total):
+        ref = _C5_CACHE["ref"][c]
+        assert counts[c] == ref.size, (c, counts[c], ref.size)
+        tol = 2e-5 if mods[c] else 1e-5
+        assert_close(got[c, :counts[c]], ref, tol=tol, what=f"channel {c} ({'FM' if mods[c] else 'AM'})")
