@@ -243,10 +243,15 @@ class SteppingFactory final : public ISteppingDriverFactory {
   REF_COUNTED(SteppingFactory);
 };
 
-// JSON "Component" (schema: reference FilterDriverFactory.cpp:181-274):
-//   {"nodes": [{"name": n, "type": t, "parameters": {...}}, ...],
-//    "connections": [{"source": n, "sourcePort": p, "sink": n, "sinkPort": p}, ...],
-//    "inputNode": n, "outputNode": n}        (inputPorts / outputPorts remapping lists are accepted in their 1:1 form)
+// JSON "Component" -- the reference's schema (FilterDriverFactory.cpp:27-179, example at :181-274):
+//   {"nodes":       {"<id>": {"type": t, <the node's own parameters inline>}, ...},
+//    "connections": [{"source": id, "sourcePort": p, "sink": id, "sinkPort": p}, ...],       (ports default to 0)
+//    "inputPorts":  [{"exposedPort": n, "mapped": {"node": id, "port": p}}, ...],            -> a PortRemappingSink
+//    "outputPorts": [{"exposedPort": n, "mapped": {"node": id, "port": p}}, ...]}            -> a PortRemappingSource
+// Each node is created from ITS OWN definition (the reference passes the whole Component text to every node factory,
+// FilterDriverFactory.cpp:51 -- a defect no node factory could work with; not reproduced).  Also accepted: "outputPort":
+// id (the key RfToPcmAudioFactory.cpp:303 emits), "inputNode" / "outputNode": id, and "nodes" as an array of
+// {"name", "type", "parameters"} (this library's first-round form).
 class FilterDriverFactory final : public IFilterDriverFactory {
  public:
   explicit FilterDriverFactory(IFactories* f) noexcept : mFactories(f) {}
@@ -264,39 +269,86 @@ class FilterDriverFactory final : public IFilterDriverFactory {
         }
       } guard {driver};
       std::map<std::string, Ref<Node>> nodes;
-      for (const Json& n : spec.at("nodes").array()) {
-        const std::string& name = n.at("name").str();
-        const std::string params = n.contains("parameters") ? n.at("parameters").dump() : "{}";
+      auto addNode = [&](const std::string& id, const Json& def, const std::string& params) -> Status {
+        if (!def.contains("type")) {
+          gsloge("Node definition for [%s] does not contain a type.", id.c_str());
+          return Status_InvalidArgument;
+        }
+        if (nodes.count(id) != 0) {
+          gsloge("Duplicate definition for node [%s].", id.c_str());
+          return Status_InvalidArgument;
+        }
         Ref<Node> node;
-        UNWRAP_OR_FWD_RESULT(node, createNode(n.at("type").str().c_str(), params.c_str()));
-        nodes.emplace(name, node);
-        FWD_IN_RESULT_IF_ERR(driver->setupNode(node.get(), name.c_str()));
+        UNWRAP_OR_FWD_STATUS(node, createNode(def.at("type").str().c_str(), params.c_str()));
+        nodes.emplace(id, node);
+        const std::string label = def.contains("description") && def.at("description").kind == Json::String ? def.at("description").str() : id;
+        return driver->setupNode(node.get(), label.c_str());
+      };
+      const Json& nodeDefs = spec.at("nodes");
+      if (nodeDefs.kind == Json::Object) {
+        for (const auto& kv : nodeDefs.members) FWD_IN_RESULT_IF_ERR(addNode(kv.first, kv.second, kv.second.dump()));
+      } else {
+        for (const Json& n : nodeDefs.array())
+          FWD_IN_RESULT_IF_ERR(addNode(n.at("name").str(), n, n.contains("parameters") ? n.at("parameters").dump() : n.dump()));
       }
-      auto find = [&](const std::string& name) -> Node* {
-        const auto it = nodes.find(name);
-        if (it == nodes.end()) throw std::invalid_argument("unknown node \"" + name + "\"");
+      auto find = [&](const std::string& id, const char* what) -> Node* {
+        const auto it = nodes.find(id);
+        if (it == nodes.end()) {
+          gsloge("Cannot %s node [%s] because it was not defined.", what, id.c_str());
+          return nullptr;
+        }
         return it->second.get().get();
       };
-      for (const Json& c : spec.at("connections").array()) {
-        Source* source = find(c.at("source").str())->asSource();
-        Sink* sink = find(c.at("sink").str())->asSink();
-        GS_REQUIRE_OR_RET_RESULT(source != nullptr && sink != nullptr, "connection endpoints must be a Source and a Sink");
-        const size_t sp = c.contains("sourcePort") ? static_cast<size_t>(c.at("sourcePort").num()) : 0;
-        const size_t kp = c.contains("sinkPort") ? static_cast<size_t>(c.at("sinkPort").num()) : 0;
-        FWD_IN_RESULT_IF_ERR(driver->connect(source, sp, sink, kp));
+      auto port = [](const Json& obj, const char* key) -> size_t { return obj.contains(key) ? static_cast<size_t>(obj.at(key).num()) : 0; };
+
+      // ---- exposed input ports -> PortRemappingSink ------------------------------------------------------------
+      if (spec.contains("inputPorts") && !spec.at("inputPorts").array().empty()) {
+        Ref<IPortRemappingSink> mapper;
+        UNWRAP_OR_FWD_RESULT(mapper, mFactories->getPortRemappingSinkFactory()->create());
+        for (const Json& m : spec.at("inputPorts").array()) {
+          const Json& mapped = m.at("mapped");
+          Node* node = find(mapped.at("node").str(), "add an input port mapping with");
+          if (node == nullptr) return ERR_RESULT(Status_NotFound);
+          GS_REQUIRE_OR_RET_RESULT_FMT(node->asSink() != nullptr, "Cannot add an input port mapping with node [%s] because it is not a sink.",
+                                       mapped.at("node").str().c_str());
+          mapper.get()->addPortMapping(port(m, "exposedPort"), node->asSink(), port(mapped, "port"));
+        }
+        driver->setDriverInput(mapper.get());
+      } else if (spec.contains("inputNode")) {
+        Node* node = find(spec.at("inputNode").str(), "use as the input");
+        if (node == nullptr) return ERR_RESULT(Status_NotFound);
+        GS_REQUIRE_OR_RET_RESULT(node->asSink() != nullptr, "the input node must be a Sink");
+        driver->setDriverInput(node->asSink());
       }
-      auto endpoint = [&](const char* direct, const char* list, const char* key) -> Node* {
-        if (spec.contains(direct)) return find(spec.at(direct).str());
-        if (spec.contains(list) && !spec.at(list).array().empty()) return find(spec.at(list).array()[0].at(key).str());
-        return nullptr;
-      };
-      if (Node* in = endpoint("inputNode", "inputPorts", "innerSink")) {
-        GS_REQUIRE_OR_RET_RESULT(in->asSink() != nullptr, "the input node must be a Sink");
-        driver->setDriverInput(in->asSink());
+      // ---- exposed output ports -> PortRemappingSource ---------------------------------------------------------
+      if (spec.contains("outputPorts") && !spec.at("outputPorts").array().empty()) {
+        Ref<IPortRemappingSource> mapper;
+        UNWRAP_OR_FWD_RESULT(mapper, mFactories->getPortRemappingSourceFactory()->create());
+        for (const Json& m : spec.at("outputPorts").array()) {
+          const Json& mapped = m.at("mapped");
+          Node* node = find(mapped.at("node").str(), "add an output port mapping with");
+          if (node == nullptr) return ERR_RESULT(Status_NotFound);
+          GS_REQUIRE_OR_RET_RESULT_FMT(node->asSource() != nullptr, "Cannot add an output port mapping with node [%s] because it is not a source.",
+                                       mapped.at("node").str().c_str());
+          mapper.get()->addPortMapping(port(m, "exposedPort"), node->asSource(), port(mapped, "port"));
+        }
+        driver->setDriverOutput(mapper.get());
+      } else if (spec.contains("outputPort") || spec.contains("outputNode")) {
+        Node* node = find(spec.at(spec.contains("outputPort") ? "outputPort" : "outputNode").str(), "use as the output");
+        if (node == nullptr) return ERR_RESULT(Status_NotFound);
+        GS_REQUIRE_OR_RET_RESULT(node->asSource() != nullptr, "the output node must be a Source");
+        driver->setDriverOutput(node->asSource());
       }
-      if (Node* out = endpoint("outputNode", "outputPorts", "innerSource")) {
-        GS_REQUIRE_OR_RET_RESULT(out->asSource() != nullptr, "the output node must be a Source");
-        driver->setDriverOutput(out->asSource());
+      // ---- connections ------------------------------------------------------------------------------------------
+      if (spec.contains("connections")) {
+        for (const Json& c : spec.at("connections").array()) {
+          Node* from = find(c.at("source").str(), "connect source");
+          Node* to = find(c.at("sink").str(), "connect sink");
+          if (from == nullptr || to == nullptr) return ERR_RESULT(Status_InvalidArgument);
+          GS_REQUIRE_OR_RET_RESULT_FMT(from->asSource() != nullptr, "Cannot connect [%s]: it is not a source.", c.at("source").str().c_str());
+          GS_REQUIRE_OR_RET_RESULT_FMT(to->asSink() != nullptr, "Cannot connect [%s]: it is not a sink.", c.at("sink").str().c_str());
+          FWD_IN_RESULT_IF_ERR(driver->connect(from->asSource(), port(c, "sourcePort"), to->asSink(), port(c, "sinkPort")));
+        }
       }
       guard.d = nullptr;
       return makeRefResultNonNull<Node>(static_cast<Node*>(driver));

@@ -167,6 +167,10 @@ GS_EXPORT Status registerDefaultNodeFactories() noexcept {
   std::call_once(g_defaultsOnce, [&]() {
     const std::pair<const char*, INodeFactory*> defaults[] = {
         {"AacFileWriter", f->getAacFileWriterFactory()},
+        {"AacWriter", f->getAacFileWriterFactory()},      // FilterFactories.cpp:136
+        {"Cosine", f->getCosineSourceFactory()},          // :140
+        {"File", f->getFileReaderFactory()},              // :141
+        {"HackRfSource", f->getHackrfSourceFactory()},    // :143
         {"AddConst", f->getAddConstFactory()},
         {"AddConstToVectorLength", f->getAddConstToVectorLengthFactory()},
         {"CosineSource", f->getCosineSourceFactory()},

@@ -9,7 +9,10 @@
 // samples of history plus any tail -- in the port buffer.  The mixer phase is a function of the ABSOLUTE sample index
 // (64-bit fixed-point turns), so it neither drifts nor depends on how the stream is chunked.
 #include <b200sdr/b200sdr.h>
+#include <gpusdrpipeline/EventPipeline.h>
 #include <gpusdrpipeline/FusedChain.h>
+
+#include <algorithm>
 
 #include <cmath>
 #include <memory>
@@ -168,13 +171,21 @@ std::vector<float> kaiserLowPass(double sampleRate, double cutoff, double transi
   return out;
 }
 
+// Parameter derivation follows RfToPcmAudioFactory.cpp:164-170 (cut-offs at 95 % / 90 % of the output Nyquist
+// frequencies, 5 % / 10 % transitions), except that the audio low-pass is designed at the rate it runs at (the
+// demodulator's output rate) -- the reference designs it at the audio rate, :185-190, which makes it an all-pass.
+void designRfToPcmTaps(float rfSampleRate, size_t rfDecim, size_t audioDecim, float rfDbAttenuation, float audioDbAttenuation,
+                       std::vector<float>& rfTaps, std::vector<float>& audioTaps) {
+  const double demodRate = static_cast<double>(rfSampleRate) / static_cast<double>(rfDecim);
+  const double audioRate = demodRate / static_cast<double>(audioDecim);
+  rfTaps = kaiserLowPass(rfSampleRate, demodRate / 2.0 * 0.95, demodRate / 2.0 * 0.05, rfDbAttenuation);
+  audioTaps = kaiserLowPass(demodRate, audioRate / 2.0 * 0.9, audioRate / 2.0 * 0.1, audioDbAttenuation);
+}
+
 class RfToPcmFactory final : public IRfToPcmAudioFactory {
  public:
   explicit RfToPcmFactory(IFactories* f) noexcept : mFactories(f) {}
 
-  // Parameter derivation follows RfToPcmAudioFactory.cpp:164-170 (cut-offs at 95 % / 90 % of the output Nyquist
-  // frequencies, 5 % / 10 % transitions), except that the audio low-pass is designed at the rate it runs at (the
-  // demodulator's output rate) -- the reference designs it at the audio rate, :185-190, which makes it an all-pass.
   Result<Filter> createRfToPcm(float rfSampleRate, Modulation modulation, size_t rfDecim, size_t audioDecim, float centerFrequency,
                                float channelFrequency, float channelWidth, float fskDeviationIfFm, float rfDbAttenuation,
                                float audioDbAttenuation, const char* commandQueueId) noexcept final {
@@ -214,9 +225,8 @@ class RfToPcmFactory final : public IRfToPcmAudioFactory {
       Ref<ICudaCommandQueue> queue;
       UNWRAP_OR_FWD_RESULT(queue, mFactories->getCommandQueueFactory()->getCudaCommandQueue(commandQueueId));
       const double demodRate = static_cast<double>(rfSampleRate) / static_cast<double>(rfDecim);
-      const double audioRate = demodRate / static_cast<double>(audioDecim);
-      const std::vector<float> rfTaps = kaiserLowPass(rfSampleRate, demodRate / 2.0 * 0.95, demodRate / 2.0 * 0.05, rfDbAttenuation);
-      const std::vector<float> audioTaps = kaiserLowPass(demodRate, audioRate / 2.0 * 0.9, audioRate / 2.0 * 0.1, audioDbAttenuation);
+      std::vector<float> rfTaps, audioTaps;
+      designRfToPcmTaps(rfSampleRate, rfDecim, audioDecim, rfDbAttenuation, audioDbAttenuation, rfTaps, audioTaps);
       GsFusedChainParams p {};
       p.structSize = sizeof(p);
       p.inputType = inputType;
@@ -246,7 +256,68 @@ class RfToPcmFactory final : public IRfToPcmAudioFactory {
 
 IRfToPcmAudioFactory* newRfToPcmAudioFactory(IFactories* f) noexcept { return new (std::nothrow) RfToPcmFactory(f); }
 
+Status designRfToPcmTapsC(float rfSampleRate, size_t rfDecim, size_t audioDecim, float rfDb, float audioDb, float* rfTaps, size_t rfCapacity,
+                          size_t* rfCount, float* audioTaps, size_t audioCapacity, size_t* audioCount) noexcept {
+  try {
+    GS_REQUIRE_OR_RET_STATUS(rfDecim > 0 && audioDecim > 0 && rfSampleRate > 0.0f, "rates and decimations must be positive");
+    std::vector<float> rf, audio;
+    designRfToPcmTaps(rfSampleRate, rfDecim, audioDecim, rfDb, audioDb, rf, audio);
+    if (rfCount != nullptr) *rfCount = rf.size();
+    if (audioCount != nullptr) *audioCount = audio.size();
+    if ((rfTaps != nullptr && rfCapacity < rf.size()) || (audioTaps != nullptr && audioCapacity < audio.size())) return Status_OutOfRange;
+    if (rfTaps != nullptr) std::copy(rf.begin(), rf.end(), rfTaps);
+    if (audioTaps != nullptr) std::copy(audio.begin(), audio.end(), audioTaps);
+    return Status_Success;
+  }
+  IF_CATCH_RETURN_STATUS
+}
+
+// ---- IEventPipeline (include/gpusdrpipeline/EventPipeline.h; reference Waiter.cpp:34-50) ---------------------------
+class EventPipeline final : public IEventPipeline {
+ public:
+  explicit EventPipeline(ICudaCommandQueue* queue) noexcept : mQueue(queue) {}
+  Status recordNextAndWaitPrevious() noexcept final {
+    CUDA_DEV_PUSH_POP_OR_RET_STATUS(mQueue->cudaDevice());
+    if (mNext == nullptr) SAFE_CUDA_OR_RET_STATUS(cudaEventCreateWithFlags(&mNext, cudaEventDisableTiming));
+    SAFE_CUDA_OR_RET_STATUS(cudaEventRecord(mNext, mQueue->cudaStream()));
+    if (mPending) SAFE_CUDA_OR_RET_STATUS(cudaEventSynchronize(mPrevious));
+    std::swap(mPrevious, mNext);
+    mPending = true;
+    return Status_Success;
+  }
+  Status waitLast() noexcept final {
+    if (!mPending) return Status_Success;
+    CUDA_DEV_PUSH_POP_OR_RET_STATUS(mQueue->cudaDevice());
+    SAFE_CUDA_OR_RET_STATUS(cudaEventSynchronize(mPrevious));
+    mPending = false;
+    return Status_Success;
+  }
+
+ private:
+  ~EventPipeline() final {
+    if (mPrevious != nullptr || mNext != nullptr) {
+      CudaDevicePushPop device(mQueue->cudaDevice());
+      if (mPrevious != nullptr) cudaEventDestroy(mPrevious);
+      if (mNext != nullptr) cudaEventDestroy(mNext);
+    }
+  }
+  ConstRef<ICudaCommandQueue> mQueue;
+  cudaEvent_t mPrevious = nullptr, mNext = nullptr;
+  bool mPending = false;
+  REF_COUNTED_NO_DESTRUCTOR(EventPipeline);
+};
+
 }  // namespace gs
+
+GS_EXPORT Status gsDesignRfToPcmTaps(float rfSampleRate, size_t rfDecim, size_t audioDecim, float rfDb, float audioDb, float* rfTaps,
+                                     size_t rfCapacity, size_t* rfCount, float* audioTaps, size_t audioCapacity, size_t* audioCount) noexcept {
+  return gs::designRfToPcmTapsC(rfSampleRate, rfDecim, audioDecim, rfDb, audioDb, rfTaps, rfCapacity, rfCount, audioTaps, audioCapacity, audioCount);
+}
+
+GS_EXPORT Result<IEventPipeline> gsCreateEventPipeline(ICudaCommandQueue* commandQueue) noexcept {
+  NON_NULL_PARAM_OR_RET(commandQueue);
+  return makeRefResultNonNull<IEventPipeline>(new (std::nothrow) gs::EventPipeline(commandQueue));
+}
 
 GS_EXPORT Result<Filter> gsCreateFusedChain(const GsFusedChainParams* params, ICudaCommandQueue* commandQueue) noexcept {
   NON_NULL_PARAM_OR_RET(params);

@@ -60,7 +60,14 @@ Status PortInput::makeRoom(size_t bytes) noexcept {
   const size_t used = mEnd - mOffset;
   if (mMemory != nullptr && mCapacity - mEnd >= bytes) return Status_Success;
   if (mMemory != nullptr && used + bytes <= mCapacity && mOffset >= used) {
-    // compact in place: source and destination do not overlap
+    // compact in place: source and destination do not overlap.  On a pinned host port the bytes in front of mOffset may
+    // still be read by a queued host->device copy (a partial drain leaves the remainder here): wait for that copy before
+    // the host overwrites them
+    if (mHost && mFencePending) {
+      CUDA_DEV_PUSH_POP_OR_RET_STATUS(mQueue->cudaDevice());
+      SAFE_CUDA_OR_RET_STATUS(cudaEventSynchronize(mFence));
+      mFencePending = false;
+    }
     FWD_IF_ERR(mCopier->copy(mMemory.get()->data(), mMemory.get()->data() + mOffset, used));
     mOffset = 0;
     mEnd = used;
@@ -646,15 +653,18 @@ class ByteCountMonitor final : public IReadByteCountMonitor {
 // ---------------------------------------------------------------------------------------------------------------
 Result<SampleType> parseSampleType(const Json& v) {
   const std::string& s = v.str();
-  if (s == "FloatComplex" || s == "floatComplex" || s == "complex") return makeValResult<SampleType>(SampleType_FloatComplex);
+  if (s == "FloatComplex" || s == "floatComplex" || s == "ComplexFloat" || s == "complex") return makeValResult<SampleType>(SampleType_FloatComplex);
   if (s == "Float" || s == "float") return makeValResult<SampleType>(SampleType_Float);
   if (s == "Int8Complex" || s == "int8Complex") return makeValResult<SampleType>(SampleType_Int8Complex);
   gsloge("Unknown sample type [%s]", s.c_str());
   return ERR_RESULT(Status_ParseError);
 }
 
+// "commandQueue" is the key the reference's node factories read (factories/FirFactory.h:32-49 etc.); "commandQueueId" is
+// the key its RfToPcmAudioFactory.cpp:223-296 writes into the Component it builds -- both are accepted
 Result<ICudaCommandQueue> queueFromJson(IFactories* f, const Json& params) {
-  return f->getCommandQueueFactory()->getCudaCommandQueue(params.at("commandQueue").str().c_str());
+  const char* key = params.contains("commandQueue") ? "commandQueue" : "commandQueueId";
+  return f->getCommandQueueFactory()->getCudaCommandQueue(params.at(key).str().c_str());
 }
 
 #define GS_JSON_CREATE_BEGIN                              \
@@ -750,9 +760,13 @@ class FirFactory final : public IFirFactory {
   GS_JSON_CREATE_BEGIN
   SampleType tapType, elementType;
   UNWRAP_OR_FWD_RESULT(tapType, parseSampleType(params.at("tapType")));
-  UNWRAP_OR_FWD_RESULT(elementType, parseSampleType(params.at("elementType")));
+  // "elementType" (FirFactory.h:40) or "signalType" (what RfToPcmAudioFactory.cpp:252,287 emits)
+  UNWRAP_OR_FWD_RESULT(elementType, parseSampleType(params.at(params.contains("elementType") ? "elementType" : "signalType")));
   std::vector<float> taps;
   for (const Json& t : params.at("taps").array()) taps.push_back(static_cast<float>(t.num()));
+  // complex taps arrive as (re, im) pairs: tapCount counts taps, not floats.  (The reference passes taps.size() floats
+  // as the tap count, FirFactory.h:44-48, and would read past the list; an odd-length list is rejected here.)
+  GS_REQUIRE_OR_RET_RESULT(tapType == SampleType_Float || taps.size() % 2 == 0, "Complex taps must be given as (re, im) pairs");
   const size_t tapCount = tapType == SampleType_Float ? taps.size() : taps.size() / 2;
   return ResultCast<Node>(createFir(tapType, elementType, static_cast<size_t>(params.at("decimation").num()), taps.data(), tapCount, queue.get()));
   GS_JSON_CREATE_END
@@ -775,9 +789,17 @@ class QuadDemodFactory final : public IQuadDemodFactory {
     }
   }
   GS_JSON_CREATE_BEGIN
-  const std::string& m = params.at("modulation").str();
-  GS_REQUIRE_OR_RET_RESULT_FMT(m == "AM" || m == "FM" || m == "am" || m == "fm", "Unknown modulation [%s]", m.c_str());
-  const bool fm = m == "FM" || m == "fm";
+  // a string (QuadDemodFactory.h:35-70) or the Modulation enum value (what RfToPcmAudioFactory.cpp:266 writes)
+  const Json& mj = params.at("modulation");
+  bool fm;
+  if (mj.kind == Json::Number) {
+    GS_REQUIRE_OR_RET_RESULT_FMT(mj.num() == Modulation_Am || mj.num() == Modulation_Fm, "Unknown modulation [%g]", mj.num());
+    fm = mj.num() == Modulation_Fm;
+  } else {
+    const std::string& m = mj.str();
+    GS_REQUIRE_OR_RET_RESULT_FMT(m == "AM" || m == "FM" || m == "am" || m == "fm", "Unknown modulation [%s]", m.c_str());
+    fm = m == "FM" || m == "fm";
+  }
   const float rate = fm ? static_cast<float>(params.at("sampleRate").num()) : 0.0f;
   const float dev = fm ? static_cast<float>(params.at("fskDeviation").num()) : 0.0f;
   return ResultCast<Node>(createQuadDemod(fm ? Modulation_Fm : Modulation_Am, rate, dev, queue.get()));

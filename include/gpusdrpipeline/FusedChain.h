@@ -37,4 +37,13 @@ struct GsFusedChainParams {
 
 GS_EXPORT [[nodiscard]] Result<Filter> gsCreateFusedChain(const GsFusedChainParams* params, ICudaCommandQueue* commandQueue) noexcept;
 
+/* The taps IRfToPcmAudioFactory::createRfToPcm() of this library designs for these parameters (Kaiser-windowed sinc of the
+ * reference's own length estimate, RfToPcmAudioFactory.cpp:44-47,164-170; the reference's designer, kernrj/remez-exchange,
+ * is not vendored), so that a caller -- and the parity tests -- can run any other implementation with IDENTICAL taps.
+ * Either taps pointer may be NULL to query the counts only.  Status_OutOfRange if a capacity is too small. */
+GS_EXPORT [[nodiscard]] Status gsDesignRfToPcmTaps(
+    float rfSampleRate, size_t rfLowPassDecimation, size_t audioLowPassDecimation, float rfLowPassDbAttenuation,
+    float audioLowPassDbAttenuation, float* rfTaps, size_t rfTapCapacity, size_t* rfTapCount, float* audioTaps, size_t audioTapCapacity,
+    size_t* audioTapCount) noexcept;
+
 #endif  // GPUSDRPIPELINE_FUSEDCHAIN_H

@@ -95,6 +95,9 @@ link() {  # link <output> <gsdr lib dir> <gsdr lib name> <sources...>
 TESTS=("$REF/tests/FirTests.cpp" "$REF/tests/CosineSourceTests.cpp" "$HERE/gtest_main.cpp")
 link "$OUT/ref_tests_naive" "$OUT" gsdr_naive "${TESTS[@]}"
 link "$OUT/ref_chain_naive" "$OUT" gsdr_naive "$HERE/ref_chain.cpp"
+# the graph driver (tests/graph_probe.cpp: SteppingDriver + nested FilterDrivers, am_test.cpp style) on the reference's own
+# host framework: what tests/test_gpu_graph.py compares this repo's drivers with
+link "$OUT/graph_probe_naive" "$OUT" gsdr_naive "$ROOT/tests/graph_probe.cpp"
 if [ -f "$B200LIB/libb200sdr.so" ]; then
   link "$OUT/ref_tests_b200" "$B200LIB" b200sdr "${TESTS[@]}"
   link "$OUT/ref_chain_b200" "$B200LIB" b200sdr "$HERE/ref_chain.cpp"
@@ -107,6 +110,7 @@ if [ -f "$B200LIB/libgpusdrpipeline.so" ]; then
         -Wl,-rpath,"$CUDA_HOME/lib64")
   "$CXX" "${FLAGS[@]}" -o "$OUT/ref_tests_ours" "${TESTS[@]}" "${OURS[@]}"
   "$CXX" "${FLAGS[@]}" -o "$OUT/ref_chain_ours" "$HERE/ref_chain.cpp" "${OURS[@]}"
+  "$CXX" "${FLAGS[@]}" -o "$OUT/graph_probe_ours" "$ROOT/tests/graph_probe.cpp" "${OURS[@]}"
   HDR=(-std=c++20 -O2 -fPIC -w -DNDEBUG -I"$ROOT/include" -I"$HERE" -I"$CUDA_HOME/include")
   "$CXX" "${HDR[@]}" -o "$OUT/ref_tests_ours_hdr" "${TESTS[@]}" "${OURS[@]}"
   "$CXX" "${HDR[@]}" -DREF_CHAIN_HAS_FUSED -o "$OUT/ref_chain_ours_hdr" "$HERE/ref_chain.cpp" "${OURS[@]}"

@@ -16,7 +16,8 @@
 #include <cuda_runtime.h>
 #include <gpusdrpipeline/Factories.h>
 #ifdef REF_CHAIN_HAS_FUSED
-#include <gpusdrpipeline/FusedChain.h>  // this repo's additive entry point: the whole chain as ONE Filter node
+#include <gpusdrpipeline/EventPipeline.h>  // this repo's additive one-deep event pipeline (the reference's private Waiter)
+#include <gpusdrpipeline/FusedChain.h>     // this repo's additive entry point: the whole chain as ONE Filter node
 #endif
 
 #include <chrono>
@@ -25,9 +26,46 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace std;
+
+// The producer side of the benchmark: every host thread writes its share of the block (a recorded stream is copied, a
+// synthetic one is generated in place: xorshift64* bytes, i.e. full-range int8 IQ noise).
+template <class Fn>
+static void parallelRange(size_t bytes, unsigned threads, Fn fn) {
+  const size_t grain = size_t(1) << 20;
+  if (threads <= 1 || bytes <= grain) {
+    fn(size_t(0), bytes);
+    return;
+  }
+  const size_t per = ((bytes + threads - 1) / threads + 63) & ~size_t(63);
+  vector<thread> pool;
+  for (unsigned t = 0; t < threads; t++) {
+    const size_t lo = t * per, hi = lo + per < bytes ? lo + per : bytes;
+    if (lo >= bytes) break;
+    pool.emplace_back([=] { fn(lo, hi); });
+  }
+  for (auto& th : pool) th.join();
+}
+static void parallelCopy(uint8_t* dst, const uint8_t* src, size_t bytes, unsigned threads) {
+  parallelRange(bytes, threads, [=](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+}
+static void parallelFill(uint8_t* dst, size_t bytes, uint64_t seed, unsigned threads) {
+  parallelRange(bytes, threads, [=](size_t lo, size_t hi) {
+    uint64_t x = seed ^ (lo * 0x9E3779B97F4A7C15ull) ^ 0x2545F4914F6CDD1Dull;
+    size_t i = lo;
+    for (; i + 8 <= hi; i += 8) {
+      x ^= x >> 12;
+      x ^= x << 25;
+      x ^= x >> 27;
+      const uint64_t v = x * 0x2545F4914F6CDD1Dull;
+      memcpy(dst + i, &v, 8);
+    }
+    for (; i < hi; i++) dst[i] = static_cast<uint8_t>(x >> (8 * (i & 7)));
+  });
+}
 
 static vector<char> readFile(const string& path) {
   FILE* f = fopen(path.c_str(), "rb");
@@ -61,6 +99,11 @@ struct Args {
   bool fused = false;
   string rftopcm;  // "api": IRfToPcmAudioFactory::createRfToPcm (cf32 input); "json": createFilter("RfToPcmAudio", ...) with int8 input
   double channelWidth = 10e3, tuned = 0.0;
+  string dumpTaps;  // --rftopcm: write the taps the factory designs to <prefix>.rf.f32 / <prefix>.audio.f32 (gsDesignRfToPcmTaps)
+  bool pipeline = false;  // --fused: alternate two pinned host buffers behind an IEventPipeline instead of a stream sync per step
+  size_t synthSamples = 0;  // --fused: no input file, this many synthetic samples per pass generated straight into the pinned block
+  size_t warmupSteps = 0;   // --fused: steps before the clock starts
+  unsigned threads = 0;     // host threads of the producer (0: all)
 };
 
 static Args parse(int argc, char** argv) {
@@ -83,13 +126,20 @@ static Args parse(int argc, char** argv) {
     else if (k == "--rftopcm") a.rftopcm = v;
     else if (k == "--channel-width") a.channelWidth = atof(v.c_str());
     else if (k == "--tuned") a.tuned = atof(v.c_str());
+    else if (k == "--dump-taps") a.dumpTaps = v;
+    else if (k == "--pipeline") a.pipeline = v != "0";
+    else if (k == "--synth-samples") a.synthSamples = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--warmup-steps") a.warmupSteps = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "--threads") a.threads = static_cast<unsigned>(strtoul(v.c_str(), nullptr, 10));
     else {
       fprintf(stderr, "unknown argument %s\n", k.c_str());
       exit(2);
     }
   }
   if (!a.rftopcm.empty()) a.fused = true;  // the factory designs its own taps
-  if ((a.rftopcm.empty() && (a.taps1.empty() || a.taps2.empty())) || a.in.empty()) {
+  if (a.threads == 0) a.threads = thread::hardware_concurrency() ? thread::hardware_concurrency() : 1;
+  if (a.threads > 32) a.threads = 32;
+  if ((a.rftopcm.empty() && (a.taps1.empty() || a.taps2.empty())) || (a.in.empty() && a.synthSamples == 0)) {
     fprintf(stderr, "--taps1, --taps2 and --in are required\n");
     exit(2);
   }
@@ -103,7 +153,7 @@ static Ref<IBuffer> request(Sink* sink, size_t port, size_t bytes) { return unwr
 int main(int argc, char** argv) {
   const Args a = parse(argc, argv);
   gslogSetVerbosity(GSLOG_WARN);
-  const vector<char> input = readFile(a.in);
+  const vector<char> input = a.in.empty() ? vector<char>() : readFile(a.in);
   const vector<float> taps1 = a.taps1.empty() ? vector<float>() : readFloats(a.taps1), taps2 = a.taps2.empty() ? vector<float>() : readFloats(a.taps2);
   const bool fm = a.mod == "fm";
 
@@ -142,6 +192,18 @@ int main(int argc, char** argv) {
       // the reference's declarative route (applications/nbfm_test.cpp:546-562): a named queue, then the factory.
       // channelFrequency - tunedFrequency = -freq, so the mixer runs at `freq` like the explicit chain above.
       const double channel = a.tuned - a.freq;
+      if (!a.dumpTaps.empty()) {
+        size_t nRf = 0, nAudio = 0;
+        THROW_IF_ERR(gsDesignRfToPcmTaps(static_cast<float>(a.fs), a.d1, a.d2, -60.0f, -60.0f, nullptr, 0, &nRf, nullptr, 0, &nAudio));
+        vector<float> rf(nRf), audio(nAudio);
+        THROW_IF_ERR(gsDesignRfToPcmTaps(static_cast<float>(a.fs), a.d1, a.d2, -60.0f, -60.0f, rf.data(), nRf, &nRf, audio.data(), nAudio, &nAudio));
+        FILE* o = fopen((a.dumpTaps + ".rf.f32").c_str(), "wb");
+        if (!o || fwrite(rf.data(), sizeof(float), nRf, o) != nRf) return 2;
+        fclose(o);
+        o = fopen((a.dumpTaps + ".audio.f32").c_str(), "wb");
+        if (!o || fwrite(audio.data(), sizeof(float), nAudio, o) != nAudio) return 2;
+        fclose(o);
+      }
       if (a.rftopcm == "api") {  // complex-float input, the reference's own signature
         chainRef = unwrap(factories->getRfToPcmAudioFactory()->createRfToPcm(
             static_cast<float>(a.fs), fm ? Modulation_Fm : Modulation_Am, a.d1, a.d2, static_cast<float>(a.tuned), static_cast<float>(channel),
@@ -159,10 +221,13 @@ int main(int argc, char** argv) {
     ConstRef<Filter> chain = chainRef;
     ConstRef<IAllocator> pinnedAlloc = unwrap(factories->getCudaAllocatorFactory()->createCudaAllocator(queue, 32, true));
     ConstRef<IBufferFactory> pinnedFactory = unwrap(factories->createBufferFactory(pinnedAlloc));
-    ConstRef<IBuffer> host = unwrap(pinnedFactory->createBuffer(a.step * 4));
+    // two pinned result buffers: with --pipeline 1 the host reads buffer i-1 while the GPU fills buffer i
+    ConstRef<IBuffer> host[2] = {unwrap(pinnedFactory->createBuffer(a.step * 4)), unwrap(pinnedFactory->createBuffer(a.step * 4))};
+    Ref<IEventPipeline> pipeline;
+    if (a.pipeline) pipeline = unwrap(gsCreateEventPipeline(queue));
     vector<float> result;
     IBuffer* o[1];
-    size_t total = 0;
+    size_t total = 0, outputs = 0;
     vector<char> cf32;  // "api" mode: the same samples as complex floats (x / 128), 8 bytes per sample
     if (a.rftopcm == "api") {
       cf32.resize(input.size() * 4);
@@ -171,13 +236,37 @@ int main(int argc, char** argv) {
     }
     const vector<char>& stream = cf32.empty() ? input : cf32;
     const size_t sampleBytes = cf32.empty() ? 2 : 8;
-    const auto start = chrono::steady_clock::now();
+    const size_t streamBytes = a.synthSamples ? a.synthSamples * sampleBytes : stream.size();
+    const bool keep = !a.out.empty();
+    auto harvest = [&](int slot) {  // the D2H copy into host[slot] has completed
+      const size_t n = host[slot]->range()->used() / sizeof(float);
+      outputs += n;
+      if (keep) result.insert(result.end(), host[slot]->readPtr<float>(), host[slot]->readPtr<float>() + n);
+    };
+    size_t stepNo = 0;
+    int pendingSlot = -1;  // result buffer whose copy was enqueued one step ago and has not been read yet
+    auto start = chrono::steady_clock::now();
+    size_t timedFrom = 0;
     for (size_t rep = 0; rep < a.repeat; rep++) {
-      for (size_t pos = 0; pos < stream.size();) {
-        size_t step = stream.size() - pos < a.step ? stream.size() - pos : a.step;
+      for (size_t pos = 0; pos < streamBytes; stepNo++) {
+        if (stepNo == a.warmupSteps && stepNo > 0) {  // allocations (pinned blocks, port buffers) happen in the first steps
+          if (pendingSlot >= 0) {
+            THROW_IF_ERR(pipeline->waitLast());
+            harvest(pendingSlot);
+            pendingSlot = -1;
+          }
+          cudaSetDevice(queue->cudaDevice());
+          cudaStreamSynchronize(queue->cudaStream());
+          timedFrom = total;
+          start = chrono::steady_clock::now();
+        }
+        size_t step = streamBytes - pos < a.step ? streamBytes - pos : a.step;
         step -= step % sampleBytes;
+        // the producer writes STRAIGHT into the copy node's pinned block (Sink contract: requestBuffer -> write -> commit):
+        // synthetic samples are generated in place, a recorded stream is copied in, both by all host threads
         Ref<IBuffer> staged = request(h2d, 0, step);
-        memcpy(staged->writePtr(), stream.data() + pos, step);
+        if (a.synthSamples) parallelFill(staged->writePtr(), step, 0x9E3779B97F4A7C15ull + stepNo, a.threads);
+        else parallelCopy(staged->writePtr(), reinterpret_cast<const uint8_t*>(stream.data()) + pos, step, a.threads);
         THROW_IF_ERR(h2d->commitBuffer(0, step));
         pos += step;
         total += step / sampleBytes;
@@ -189,16 +278,36 @@ int main(int argc, char** argv) {
         o[0] = d2hIn.get();
         THROW_IF_ERR(chain->readOutput(o, 1));
         THROW_IF_ERR(d2h->commitBuffer(0, d2hIn->range()->used()));
-        while (d2h->getOutputDataSize(0) > 0) {
-          host->range()->clearRange();
-          o[0] = host.get();
-          THROW_IF_ERR(d2h->readOutput(o, 1));
-          cudaSetDevice(queue->cudaDevice());
-          cudaStreamSynchronize(queue->cudaStream());
-          const float* ptr = host->readPtr<float>();
-          result.insert(result.end(), ptr, ptr + host->range()->used() / sizeof(float));
+        const int slot = static_cast<int>(stepNo & 1);
+        host[slot]->range()->clearRange();
+        o[0] = host[slot].get();
+        THROW_IF_ERR(d2h->readOutput(o, 1));
+        if (pipeline != nullptr && d2h->getOutputDataSize(0) == 0) {
+          // one-deep pipeline (the reference's Waiter, src/filters/Waiter.cpp:34-50): wait for the PREVIOUS step only
+          THROW_IF_ERR(pipeline->recordNextAndWaitPrevious());
+          if (pendingSlot >= 0) harvest(pendingSlot);
+          pendingSlot = slot;
+        } else {
+          if (pendingSlot >= 0) {
+            THROW_IF_ERR(pipeline->waitLast());
+            harvest(pendingSlot);
+            pendingSlot = -1;
+          }
+          for (;;) {  // a stream sync per step, as nbfm_test.cpp:346-347 does (also: a result larger than the host buffer)
+            cudaSetDevice(queue->cudaDevice());
+            cudaStreamSynchronize(queue->cudaStream());
+            harvest(slot);
+            if (d2h->getOutputDataSize(0) == 0) break;
+            host[slot]->range()->clearRange();
+            THROW_IF_ERR(d2h->readOutput(o, 1));
+          }
+          host[slot]->range()->clearRange();
         }
       }
+    }
+    if (pendingSlot >= 0) {
+      THROW_IF_ERR(pipeline->waitLast());
+      harvest(pendingSlot);
     }
     const double secs = chrono::duration<double>(chrono::steady_clock::now() - start).count();
     if (!a.out.empty()) {
@@ -206,8 +315,10 @@ int main(int argc, char** argv) {
       if (!f || fwrite(result.data(), sizeof(float), result.size(), f) != result.size()) return 2;
       fclose(f);
     }
-    printf("{\"samples\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, \"repeat\": %zu, \"fused\": true}\n",
-           total, result.size(), secs, static_cast<double>(total) / secs / 1e6, a.step, a.repeat);
+    printf("{\"samples\": %zu, \"timed_samples\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, \"repeat\": %zu, "
+           "\"fused\": true, \"pipeline\": %s, \"threads\": %u, \"source\": \"%s\"}\n",
+           total, total - timedFrom, outputs, secs, static_cast<double>(total - timedFrom) / secs / 1e6, a.step, a.repeat, a.pipeline ? "true" : "false",
+           a.threads, a.synthSamples ? "synthetic, generated in place" : "file");
     return 0;
 #else
     fprintf(stderr, "--fused needs this repo's headers (REF_CHAIN_HAS_FUSED)\n");

@@ -70,6 +70,29 @@ int main() {
   if (f->getCommandQueueFactory()->exists("q0")) return 19;
   if (f->getCommandQueueFactory()->getCudaCommandQueue("q0").status != Status_NotFound) return 20;
 
+  // "Component" descriptions in the reference's schema (FilterDriverFactory.cpp:27-179) parse without a GPU as long as no
+  // GPU node has to be built: nodes as an OBJECT keyed by id, exposedPort/mapped{node,port} lists, the documented statuses
+  {
+    Result<Node> empty = createNode("Component", "{\"nodes\": {}, \"connections\": [], \"inputPorts\": [], \"outputPorts\": []}");
+    if (empty.status != Status_Success || empty.value == nullptr) return 30;
+    ConstRef<Node> hold(empty.value);
+    if (hold->asFilter() == nullptr || hold->asDriver() == nullptr) return 31;
+  }
+  if (createNode("Component", "{\"connections\": []}").status != Status_ParseError) return 32;  // "nodes" is required
+  if (createNode("Component", "{\"nodes\": {\"a\": {\"description\": \"no type\"}}}").status != Status_InvalidArgument) return 33;
+  if (createNode("Component", "{\"nodes\": {\"a\": {\"type\": \"nope\"}}}").status != Status_NotFound) return 34;
+  if (createNode("Component", "{\"nodes\": {}, \"inputPorts\": [{\"exposedPort\": 0, \"mapped\": {\"node\": \"ghost\", \"port\": 1}}]}").status !=
+      Status_NotFound)
+    return 35;
+  if (createNode("Component", "{\"nodes\": {}, \"connections\": [{\"source\": \"a\", \"sink\": \"b\"}]}").status != Status_InvalidArgument) return 36;
+  // a nested Component is a node like any other (ids are per Component)
+  if (createNode("Component", "{\"nodes\": {\"inner\": {\"type\": \"Component\", \"nodes\": {}}}, \"outputPort\": \"inner\"}").status != Status_Success)
+    return 37;
+  // the reference's registry names (FilterFactories.cpp:132-150) all resolve
+  for (const char* name : {"AacWriter", "AddConst", "AddConstToVectorLength", "Component", "Cosine", "File", "Fir", "HackRfSource", "Int8ToFloat",
+                           "Magnitude", "MultiplyCCC", "QuadDemod"})
+    if (!hasNodeFactory(name)) return 38;
+
   // no CPU fallback: with no CUDA device every GPU-facing creation fails with a Status, never with a crash
   int deviceCount = 0;
   if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0) {

@@ -24,8 +24,12 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 
 
 def _need(name):
+    """oracle/_ref is built where /root/reference is mounted (__graft_entry__.build()) and travels with the repo snapshot.
+    A partly built directory is an error, not a reason to skip; only a checkout that never saw the reference skips."""
     path = os.path.join(REF, name)
     if not os.path.exists(path):
+        if os.path.isdir(REF) and os.listdir(REF):
+            pytest.fail(f"{path} is missing although oracle/_ref was built: re-run __graft_entry__.build()")
         pytest.skip(f"{path} not built (oracle/ref/build_ref.sh needs /root/reference; run __graft_entry__.build())")
     return path
 
@@ -75,7 +79,8 @@ def test_chain_through_reference_api(tmp_path, mod):
         fused_big = _run_chain(exe, tmp_path, "fused_big", x, t1, d1, t2, d2, mod, fs, freq, step=3 << 20, extra=("--fused", "1"))
         assert np.array_equal(fused[0], fused_big[0]), "the fused node's output must not depend on the step size"
     if "naive" not in results or len(results) < 2:
-        pytest.skip("oracle/_ref chain drivers not built")
+        _need("ref_chain_naive")
+        _need("ref_chain_ours_hdr")
     ref, info = results["naive"]
     # stream totals are chunking independent: floor((N - (T-1)) / D) per FIR, one sample held by the FM discriminator
     n_rf = orc.fir_num_outputs(n, 101, d1)
@@ -108,14 +113,12 @@ def test_chain_through_reference_api(tmp_path, mod):
 
 
 @pytest.mark.parametrize("route", ["api", "json"])
-def test_rf_to_pcm_factory_demodulates_an_am_tone(tmp_path, route):
+def test_rf_to_pcm_factory_matches_the_oracle_with_its_own_taps(tmp_path, route):
     """SURVEY 8(f) rank 1: the declarative caller.  IRfToPcmAudioFactory::createRfToPcm (complex-float input, the reference's
     signature: FilterFactories.h:159-175) and createFilter("RfToPcmAudio", json) with the additive int8 input both return ONE
     fused Filter that designs its own taps; a carrier 1.234 MHz off the tuned frequency, amplitude-modulated by a 1 kHz
     tone, must come out as that tone at 48 kHz, and the two routes must agree."""
-    exe = os.path.join(REF, "ref_chain_ours_hdr")
-    if not os.path.exists(exe):
-        pytest.skip("oracle/_ref chain drivers not built")
+    exe = _need("ref_chain_ours_hdr")
     fs, off, d1, d2 = 19.2e6, 1.234e6, 40, 10
     n = 1 << 22
     t = np.arange(n) / fs
@@ -128,10 +131,11 @@ def test_rf_to_pcm_factory_demodulates_an_am_tone(tmp_path, route):
     src = tmp_path / "in.i8"
     x.tofile(src)
 
-    def run(which):
-        out = tmp_path / f"out_{which}.f32"
+    def run(which, pipeline="0"):
+        out = tmp_path / f"out_{which}_{pipeline}.f32"
         cmd = [exe, "--fs", repr(fs), "--freq", repr(-off), "--mod", "am", "--d1", str(d1), "--d2", str(d2), "--in", str(src), "--out", str(out),
-               "--rftopcm", which, "--tuned", "100e6", "--channel-width", "10e3", "--step", str(1 << 20)]
+               "--rftopcm", which, "--tuned", "100e6", "--channel-width", "10e3", "--step", str(1 << 20), "--dump-taps", str(tmp_path / which),
+               "--pipeline", pipeline]
         res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
         assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]
         return np.fromfile(out, dtype=np.float32)
@@ -144,8 +148,24 @@ def test_rf_to_pcm_factory_demodulates_an_am_tone(tmp_path, route):
     assert abs(peak_hz - 1e3) <= 10.0, peak_hz
     # envelope 60/128 * (1 +- 0.5) through unity-gain low-passes
     assert abs(seg.mean() - 60.0 / 128.0) < 0.02 and abs((seg.max() - seg.min()) / 2 - 30.0 / 128.0) < 0.02
+    # against the fp64 oracle run with the taps the factory designed (gsDesignRfToPcmTaps): the whole stream, exact count
+    from oracle import oracle as orc
+    t1 = np.fromfile(tmp_path / f"{route}.rf.f32", dtype=np.float32)
+    t2 = np.fromfile(tmp_path / f"{route}.audio.f32", dtype=np.float32)
+    assert t1.size % 2 == 1 and t2.size % 2 == 1 and abs(t1.sum() - 1.0) < 1e-5 and abs(t2.sum() - 1.0) < 1e-5
+    if route == "json":
+        spec_o = orc.ChainSpec(fs, -off, t1, d1, orc.AM, 1.0, t2, d2)
+        gold, _, _ = orc.chain(spec_o, x)
+    else:  # createRfToPcm takes complex float: the same samples as x / 128
+        zf = (x.astype(np.float32) * np.float32(1.0 / 128.0)).view(np.complex64)
+        spec_o = orc.ChainSpec(fs, -off, t1, d1, orc.AM, 1.0, t2, d2, input_int8=False)
+        gold, _, _ = orc.chain(spec_o, zf)
+    assert audio.size == gold.size, (audio.size, gold.size)
+    assert_close(audio, gold, REL_TOL, f"RfToPcmAudio ({route}) vs fp64 oracle with the factory's taps")
+    # the one-deep event pipeline on the host side (IEventPipeline = the reference's Waiter) changes nothing in the stream
+    piped = run(route, pipeline="1")
+    assert np.array_equal(piped, audio)
     if route == "json":  # the int8 route (toepKernel) against the complex-float route (rows kernels): same taps, same stream
         other = run("api")
-        m = min(audio.size, other.size)
-        assert abs(audio.size - other.size) <= 1
-        assert_close(audio[:m], other[:m], REL_TOL, "RfToPcmAudio json (int8) vs createRfToPcm (cf32)")
+        assert other.size == audio.size
+        assert_close(audio, other, REL_TOL, "RfToPcmAudio json (int8) vs createRfToPcm (cf32)")
