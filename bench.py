@@ -3,21 +3,26 @@
 
   python bench.py --gpus N --steps K --warmup W            # our arm (hand-written sm_100a kernels)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the fp64 oracle port on host cores
+  python bench.py --workload wbfm|channelizer|firsweep     # BASELINE configs C3 / C5 / C4 as their own lines
 
-Workload = BASELINE.json configs[1] (C2, AM broadcast chain): per GPU and per step one block of 2^28
-synthetic int8 IQ samples (512 MiB, larger than L2, so no L2 flush is needed between iterations)
--> mix by -1.234 MHz -> 101-tap low-pass, decimate by 40 -> |.| -> 129-tap low-pass, decimate by 10
--> 48 kHz-class audio.  At N > 1 every rank processes its own time segment of one long stream
-(no collective on the filter path) and the decimated audio is gathered to rank 0 over NCCL inside the
-timed region; per-GPU work is fixed, so scaling is "weak".
+Default workload = BASELINE.json configs[1] (C2, AM broadcast chain): per GPU and per step one block of 2^28 synthetic
+int8 IQ samples (512 MiB, larger than L2, so no L2 flush is needed between iterations) -> mix by -1.234 MHz -> 101-tap
+low-pass, decimate by 40 -> |.| -> 129-tap low-pass, decimate by 10 -> 48 kHz-class audio.  At N > 1 every rank processes
+its own time segment of one long stream (no collective on the filter path) and the decimated audio is gathered to rank 0
+inside the timed region by the library's b200sdr_gather (NCCL send/recv on a side stream, include/b200sdr/b200sdr.h);
+per-GPU work is fixed, so scaling is "weak".  Every line also carries a `channelizer` sub-record: BASELINE configs[4]
+(C5, 256 channels) on the same N GPUs, strong scaling, with the same workload timed on ONE GPU in the same run.
 
-One JSON line is printed by rank 0 (see the task contract for the keys).
+torch / torch.distributed are plumbing here (device memory, rendezvous of the NCCL id, barriers); the timed work is this
+repo's kernels behind the C-ABI.  One JSON line is printed by rank 0 (see the task contract for the keys).
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
+import shutil
 import statistics
 import subprocess
 import sys
@@ -42,43 +47,61 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--warmup-seconds", type=float, default=0.5,
-                    help="keep running untimed warm-up steps until this much wall time has passed (a step is ~0.2 ms; "
-                         "the SM clock needs far longer than 3 steps to leave its idle state)")
+                    help="also keep running untimed warm-up steps until this much wall time has passed (a step is ~0.1 ms; "
+                         "the SM clock needs far longer than 3 steps to leave its idle state); reported as warmup_extra_steps")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--log2-block", type=int, default=LOG2_BLOCK, help="log2 of input samples per GPU per step")
-    ap.add_argument("--workload", choices=["am", "wbfm", "channelizer"], default="am")
-    ap.add_argument("--channels", type=int, default=256, help="channelizer workload: total channels (sharded over the GPUs)")
+    ap.add_argument("--workload", choices=["am", "wbfm", "channelizer", "firsweep"], default="am")
+    ap.add_argument("--channels", type=int, default=256, help="channelizer workload: total channels")
     ap.add_argument("--shard", choices=["auto", "channels", "time"], default="auto",
                     help="channelizer workload, N > 1: shard by channel or by time segment (auto: time on the filter-bank route)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-channelizer", action="store_true", help="leave the C5 sub-record out of an am/wbfm line")
+    ap.add_argument("--skip-ncu", action="store_true", help="do not measure roofline.traffic with ncu (use the committed capture)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
 
 
+def load_taps_module():
+    """cuda_sdr_b200/taps.py by path: pure numpy, and importing it this way does not load libb200sdr.so (the reference arm
+    must not map the product library)."""
+    spec = importlib.util.spec_from_file_location("_b200sdr_taps", os.path.join(ROOT, "cuda_sdr_b200", "taps.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def fm_gain_f32(input_sample_rate: float, deviation: float) -> float:
+    """QuadDemodFactory.h:108-110 in float32 (same expression as cuda_sdr_b200.fm_gain, restated so that the reference arm
+    needs no product import)."""
+    import math
+    import numpy as np
+    f = np.float32
+    return float(f(input_sample_rate) / (f(2.0) * f(math.pi) * f(deviation) * f(5)))
+
+
 def workload(name: str):
-    from cuda_sdr_b200 import taps
+    taps = load_taps_module()
     if name == "am":
         return dict(name="C2 AM broadcast chain", fs=FS, f=F_SHIFT, t1=taps.lowpass(T1, 0.45 * FS / D1, FS), d1=D1, mod=0, gain=1.0,
                     t2=taps.lowpass(T2, 0.45 * 48e3, FS / D1), d2=D2)
-    from cuda_sdr_b200 import fm_gain
-    return dict(name="C3 WBFM chain", fs=FS, f=2.5e6, t1=taps.lowpass(545, 100e3, FS), d1=80, mod=1, gain=fm_gain(FS / 80, 75e3),
+    return dict(name="C3 WBFM chain", fs=FS, f=2.5e6, t1=taps.lowpass(545, 100e3, FS), d1=80, mod=1, gain=fm_gain_f32(FS / 80, 75e3),
                 t2=taps.lowpass(273, 0.45 * 48e3, FS / 80), d2=5)
 
 
-def config_dict(args, wl, extra=None):
-    n = 1 << args.log2_block
+def config_dict(wl, log2_samples, extra=None):
+    """`workload` names the chain (identical in both arms); the block one step processes is a separate key, because the CPU arm
+    runs a bounded sample of the GPU arm's block (the metric is a rate)."""
+    n = 1 << log2_samples
     cfg = {
-        "workload": f"{wl['name']}: 2^{args.log2_block} synthetic int8 IQ samples per GPU per step at {wl['fs'] / 1e6:.1f} Msps-class rate "
+        "workload": f"{wl['name']}: synthetic int8 IQ at a {wl['fs'] / 1e6:.1f} Msps-class rate "
                     f"-> mix -> {len(wl['t1'])}-tap FIR decimate-by-{wl['d1']} -> {'AM' if wl['mod'] == 0 else 'FM'} demod -> "
                     f"{len(wl['t2'])}-tap audio FIR decimate-by-{wl['d2']}",
         "samples_per_gpu_per_step": n,
         "rf_taps": len(wl["t1"]), "rf_decimation": wl["d1"], "audio_taps": len(wl["t2"]), "audio_decimation": wl["d2"],
         "modulation": "am" if wl["mod"] == 0 else "fm",
         "phase_mode": "exact (64-bit fixed-point turns)",
-        "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
-        "parallelism": "overlapped time segments, one per GPU; NCCL send/recv gather of the audio to rank 0 on a side stream, "
-                       "overlapping the next step's kernel",
     }
     if extra:
         cfg.update(extra)
@@ -86,7 +109,7 @@ def config_dict(args, wl, extra=None):
 
 
 # ---------------------------------------------------------------------------------------------------
-# clocks sampling (nvidia-smi in the background during the timed region)
+# clocks sampling (nvidia-smi in the background during the timed region), one sampler per rank
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -100,7 +123,7 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -137,11 +160,18 @@ class ClockSampler:
                 "power_w_max": hi}
 
 
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (fp64, OpenMP) on a bounded sample of the same workload
 # ---------------------------------------------------------------------------------------------------
 def cpu_chain_rate(wl, target_seconds: float, max_log2: int = 26):
-    """Returns (Msps, cores, sample description, samples, seconds) for the fp64 oracle on host cores."""
+    """Returns (Msps, cores, sample description) for the fp64 oracle on host cores."""
     import numpy as np
     from oracle import oracle as orc
 
@@ -160,54 +190,43 @@ def cpu_chain_rate(wl, target_seconds: float, max_log2: int = 26):
     out, _, _ = orc.chain(spec, x)
     dt = time.perf_counter() - t0
     assert out.size == spec.num_outputs(n)
-    return n / dt / 1e6, orc.num_threads(), f"2^{log2} samples of the same workload, one pass, fp64 oracle (oracle/oracle.c), OpenMP", n, dt
+    return n / dt / 1e6, orc.num_threads(), f"2^{log2} samples of the same workload, one pass, fp64 oracle (oracle/oracle.c), OpenMP"
 
 
-def reference_api_rates(wl, log2_samples: int = 24):
-    """Throughput of the chain driven through the REFERENCE'S Filter API in <= 1 MiB steps, host buffers in and out
-    (oracle/ref/ref_chain.cpp, built by oracle/ref/build_ref.sh into oracle/_ref/):
-      reference_cuda_pipeline : the reference's own host framework (compiled in place) + a plain restated gsdr  (= B1)
-      ours_filter_api_fused   : this repo's libgpusdrpipeline.so, the same Filter contract, ONE fused node, 4 MiB steps
-    Returns {} when the binaries are not there (they need /root/reference at build time)."""
+def reference_pipeline_rate(wl, log2_samples: int = 24):
+    """Baseline B1: the reference's own host framework compiled in place + a plain restated gsdr, driven in
+    <= 1 MiB steps through its Filter API with pinned host buffers (oracle/ref/ref_chain.cpp -> oracle/_ref/ref_chain_naive).
+    A reported baseline, like cpu_baseline; {} when the binary is not there (it needs /root/reference at build time)."""
     import numpy as np
 
-    out = {}
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    naive, ours = os.path.join(ref_dir, "ref_chain_naive"), os.path.join(ref_dir, "ref_chain_ours_hdr")
-    if not os.path.exists(naive) and not os.path.exists(ours):
-        return out
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_chain_naive")
+    if not os.path.exists(exe):
+        return {}
     n = 1 << log2_samples
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
         rng = np.random.default_rng(0x5D120001)
         rng.integers(-100, 101, size=2 * n, dtype=np.int8).tofile(os.path.join(tmp, "in.i8"))
         np.asarray(wl["t1"], dtype=np.float32).tofile(os.path.join(tmp, "t1.f32"))
         np.asarray(wl["t2"], dtype=np.float32).tofile(os.path.join(tmp, "t2.f32"))
-        base = ["--fs", repr(wl["fs"]), "--freq", repr(wl["f"]), "--mod", "am" if wl["mod"] == 0 else "fm", "--d1", str(wl["d1"]),
-                "--d2", str(wl["d2"]), "--taps1", os.path.join(tmp, "t1.f32"), "--taps2", os.path.join(tmp, "t2.f32"),
-                "--in", os.path.join(tmp, "in.i8")]
-        runs = [("reference_cuda_pipeline", naive, ["--repeat", "4"],
-                 "reference host framework compiled in place + restated one-thread-per-output gsdr kernels (B1), <= 1 MiB steps, "
-                 "pinned host in / host out"),
-                ("ours_filter_api_fused", ours, ["--repeat", "16", "--fused", "1", "--step", str(4 << 20)],
-                 "this repo's libgpusdrpipeline.so through the same Filter contract: CudaMemcpy -> ONE fused node -> CudaMemcpy, "
-                 "4 MiB steps")]
-        for key, exe, extra, what in runs:
-            if not os.path.exists(exe):
-                continue
-            try:
-                res = subprocess.run([exe] + base + extra, capture_output=True, text=True, timeout=300)
-                info = json.loads(res.stdout.strip().splitlines()[-1])
-                out[key] = {"value": info["msps"], "unit": UNIT, "samples": info["samples"], "what": what}
-            except Exception as e:  # a baseline, never fatal for the bench line
-                out[key] = {"value": None, "error": str(e)[:200]}
-    return out
+        cmd = [exe, "--fs", repr(wl["fs"]), "--freq", repr(wl["f"]), "--mod", "am" if wl["mod"] == 0 else "fm", "--d1", str(wl["d1"]),
+               "--d2", str(wl["d2"]), "--taps1", os.path.join(tmp, "t1.f32"), "--taps2", os.path.join(tmp, "t2.f32"),
+               "--in", os.path.join(tmp, "in.i8"), "--repeat", "4"]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            info = json.loads(res.stdout.strip().splitlines()[-1])
+            return {"reference_cuda_pipeline": {
+                "value": info["msps"], "unit": UNIT, "samples": info["samples"],
+                "what": "reference host framework compiled in place + restated one-thread-per-output gsdr kernels (B1), <= 1 MiB steps, "
+                        "pinned host in / host out"}}
+        except Exception as e:  # a baseline, never fatal for the bench line
+            return {"reference_cuda_pipeline": {"value": None, "error": str(e)[:200]}}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    wl = workload(args.workload)
+    wl = workload("wbfm" if args.workload == "wbfm" else "am")
     import numpy as np
     from oracle import oracle as orc
 
@@ -234,13 +253,16 @@ def run_reference_arm(args):
         orc.chain(spec, x)
     dt = time.perf_counter() - t0
     msps = n * args.steps / dt / 1e6
-    sample = f"each step = 2^{log2} samples of the workload (bounded sample), fp64 oracle port on host cores, OpenMP"
+    sample = f"each step = 2^{log2} samples of the workload (a bounded sample of the 2^{args.log2_block}-sample block the GPU arm runs), " \
+             "fp64 oracle port on host cores, OpenMP"
     line = {
         "impl": "reference", "metric": METRIC, "value": msps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_dict(args, wl, {"note": "the reference has no CPU DSP path and its kernels (gsdr) are absent; this arm is the "
-                                                  "repo's CPU restatement (oracle port), not the reference's CUDA pipeline"}),
+        "config": config_dict(wl, log2, extra={
+            "bounded_sample_of_samples_per_gpu_per_step": 1 << args.log2_block,
+            "l2": "n/a (host arm)", "parallelism": "host cores, OpenMP",
+            "kernel_variant": "fp64 CPU restatement (oracle/oracle.c): the reference has no CPU DSP path and its kernels (gsdr) are absent"}),
         "cpu_baseline": {"value": msps, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": msps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -250,166 +272,276 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------
-# our arm
+# shared plumbing of the GPU arms
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one rank: device, torch.distributed (rendezvous + barriers only), the NCCL id for b200sdr_gather."""
 
-    import cuda_sdr_b200 as sdr
-    from cuda_sdr_b200 import sharding
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL prints its version banner on stdout when the communicator comes up; stdout must carry ONE JSON line, so fd 1
-        # points at stderr until the first collective has run
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # NCCL prints its version banner on stdout when the communicator comes up; stdout must carry ONE JSON line, so fd 1
+            # points at stderr until the communicators exist
+            sys.stdout.flush()
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.all_reduce(torch.zeros(1, device=self.dev))
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
+
+    def make_gather(self, floats_per_rank, slabs=3):
+        """b200sdr_gather over all ranks; the 128-byte NCCL id travels from rank 0 through torch.distributed."""
+        from cuda_sdr_b200 import sharding
+        torch, dist = self.torch, self.dist
+        uid = None
+        if self.world > 1:
+            t = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+            if self.rank == 0:
+                t.copy_(torch.frombuffer(bytearray(sharding.Gather.unique_id()), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            uid = bytes(t.cpu().numpy().tobytes())
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
-            probe = torch.zeros(1, device=dev)
-            dist.all_reduce(probe)
-            torch.cuda.synchronize()
+            return sharding.Gather(self.rank, self.world, floats_per_rank, slabs=slabs, device=self.local_rank, unique_id=uid)
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, value: float) -> float:
+        if self.world == 1:
+            return value
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure_traffic_with_ncu(wl, log2_block, variant):
+    """DRAM bytes of ONE launch of the chain kernel (dram__bytes_read.sum + dram__bytes_write.sum) from a live ncu pass over a
+    one-step child process.  None when ncu is missing or fails; the caller then falls back to the committed capture."""
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    child = (
+        "import sys, torch; sys.path.insert(0, %r); import bench, cuda_sdr_b200 as sdr\n"
+        "wl = bench.workload(%r); n = 1 << %d; dev = torch.device('cuda', 0)\n"
+        "c = sdr.Chain(wl['fs'], wl['f'], wl['t1'], wl['d1'], wl['mod'], fm_gain=wl['gain'], audio_taps=wl['t2'], audio_decim=wl['d2'])\n"
+        "x = sdr.synth.device_int8_iq(n, dev); c.process_device(x); c.process_device(x); torch.cuda.synchronize()\n"
+    ) % (ROOT, "am" if wl["mod"] == 0 else "wbfm", log2_block)
+    kernel = "toepKernel" if variant.startswith("toeplitz<") else "chainKernel"
+    try:
+        res = subprocess.run([ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", f"regex:{kernel}",
+                              "-s", "1", "-c", "1", "--csv", sys.executable, "-c", child], capture_output=True, text=True, timeout=240)
+        total, unit_scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        found = 0
+        for line in res.stdout.splitlines():
+            cells = [c.strip('"') for c in line.split('","')]
+            if len(cells) >= 3 and ("dram__bytes_read.sum" in cells or "dram__bytes_write.sum" in cells):
+                value, unit = float(cells[-1].replace(",", "")), cells[-2]
+                total += value * unit_scale.get(unit, 1.0)
+                found += 1
+        return total if found == 2 else None
+    except Exception:
+        return None
+
+
+def e2e_filter_api(ctx, wl):
+    """The headline end-to-end number: build/bin/filter_api_bench (tools/filter_api_bench.cpp) drives host -> CudaMemcpyFilter ->
+    ONE fused Filter -> CudaMemcpyFilter -> host through the reference-facing IFactories / Filter API, one process per GPU."""
+    import numpy as np
+
+    exe = os.path.join(ROOT, "build", "bin", "filter_api_bench")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
+        np.asarray(wl["t1"], dtype=np.float32).tofile(os.path.join(tmp, "t1.f32"))
+        np.asarray(wl["t2"], dtype=np.float32).tofile(os.path.join(tmp, "t2.f32"))
+        threads = max(1, len(os.sched_getaffinity(0)) // max(1, ctx.world))
+        if ctx.world > 1:
+            threads = max(threads, 4)  # torchrun pins nothing; leave the producer a few threads per rank
+        cmd = [exe, "--fs", repr(wl["fs"]), "--freq", repr(wl["f"]), "--mod", "am" if wl["mod"] == 0 else "fm", "--d1", str(wl["d1"]),
+               "--d2", str(wl["d2"]), "--taps1", os.path.join(tmp, "t1.f32"), "--taps2", os.path.join(tmp, "t2.f32"), "--device", str(ctx.local_rank),
+               "--samples-per-pass", str(1 << 28), "--passes", "6", "--step", str(64 << 20), "--warmup-steps", "4", "--pipeline", "1",
+               "--threads", str(threads)]
+        ctx.barrier()
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            info = json.loads(res.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            info = {"error": str(e)[:200]}
+    infos = ctx.gather_objects(info)
+    if ctx.rank != 0:
+        return None
+    if any("error" in i for i in infos):
+        return {"value": None, "unit": UNIT, "error": next(i["error"] for i in infos if "error" in i)}
+    secs = max(i["seconds"] for i in infos)
+    samples = sum(i["timed_samples"] for i in infos)
+    steps = infos[0]["timed_steps"]
+    return {"value": samples / secs / 1e6, "unit": UNIT, "h2d_bytes_per_step": infos[0]["h2d_bytes"] // max(1, steps),
+            "d2h_bytes_per_step": infos[0]["d2h_bytes"] // max(1, steps), "steps": steps,
+            "api": "IFactories fused Filter: host producer -> CudaMemcpyFilter (pinned, H2D) -> gsCreateFusedChain Filter -> CudaMemcpyFilter (D2H) "
+                   "-> pinned host buffers behind IEventPipeline; 64 MiB steps (tools/filter_api_bench.cpp), one process per GPU",
+            "producer_threads_per_gpu": infos[0]["threads"], "per_rank_msps": [i["msps"] for i in infos]}
+
+
+# ---------------------------------------------------------------------------------------------------
+# C2 / C3: the chain, weak scaling over time segments
+# ---------------------------------------------------------------------------------------------------
+def run_chain(args, ctx):
+    import cuda_sdr_b200 as sdr
+
+    torch = ctx.torch
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     wl = workload(args.workload)
     n = 1 << args.log2_block
     chain = sdr.Chain(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], fm_gain=wl["gain"], audio_taps=wl["t2"], audio_decim=wl["d2"],
-                      device=local_rank)
+                      device=ctx.local_rank)
     n_rf, n_demod, n_audio = chain.counts(n)
     x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120001 + rank)  # this rank's time segment of the stream
     demod = torch.empty(n_demod, dtype=torch.float32, device=dev)
-    # Audio of GATHER_EVERY consecutive steps is collected in one of two slabs; a full slab is gathered to rank 0 with ONE
-    # batched send/recv on a side stream while the next slab fills (the exchange is ~1 % of the input bytes: what it costs
-    # is host-side enqueue time per call, hence the batching)
-    GATHER_EVERY = int(os.environ.get("BENCH_GATHER_EVERY", "32"))  # measured at N = 2: 8 -> 0.1065, 32 -> 0.1043, 64 -> 0.1042 ms/step
-    slabs = [torch.empty(GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
     first_index = rank * n  # absolute sample index of the segment (mixer phase)
-    gathered = [torch.empty(world, GATHER_EVERY, n_audio, dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else None
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    slab_full = [torch.cuda.Event() for _ in range(2)]
-    slab_drained = [torch.cuda.Event() for _ in range(2)]
+    # Audio of GATHER_EVERY consecutive steps is collected in one of three slabs; a full slab is gathered to rank 0 by ONE grouped
+    # NCCL send/recv on the library's side stream while the next slabs fill.  The cadence follows the run length so that at most
+    # ~1/4 of the audio can still be in flight when the last kernel ends.
+    ge = int(os.environ.get("BENCH_GATHER_EVERY", "0")) or max(1, min(32, args.steps // 4))
+    slabs = 3
+    gather = ctx.make_gather([ge * n_audio] * world, slabs) if world > 1 else None
+    if gather is not None:
+        views = [gather.slab(s).view(ge, n_audio) for s in range(slabs)]
+    else:
+        views = [torch.empty(ge, n_audio, dtype=torch.float32, device=dev) for _ in range(slabs)]
     step_no = [0]
-
-    def gather(slab, count):
-        """Decimated audio of every rank -> rank 0 (the only exchange on the path), on the side stream."""
-        if world == 1:
-            return
-        slab_full[slab].record()
-        with torch.cuda.stream(comm_stream):
-            comm_stream.wait_event(slab_full[slab])
-            if rank == 0:
-                gathered[slab][0, :count].copy_(slabs[slab][:count], non_blocking=True)
-                ops = [dist.P2POp(dist.irecv, gathered[slab][r, :count], r) for r in range(1, world)]
-            else:
-                ops = [dist.P2POp(dist.isend, slabs[slab][:count], 0)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-            slab_drained[slab].record()
-
-    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     fused = chain.fused
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def step(i=None, last=False):
         k = step_no[0]
         step_no[0] += 1
-        slab, slot = (k // GATHER_EVERY) & 1, k % GATHER_EVERY
-        if world > 1 and slot == 0:
-            torch.cuda.current_stream().wait_event(slab_drained[slab])  # this slab's previous gather has drained
+        slab, slot = (k // ge) % slabs, k % ge
+        if gather is not None and slot == 0:
+            gather.acquire(slab)  # this slab's previous gather has drained
         if i is not None and not fused:
-            k1_events[i][0].record()
-        got = chain.process_device(x, first_index, out=slabs[slab][slot], scratch=demod)  # fused: ONE kernel; else K1 + K2
+            k_events[i][0].record()
+        got = chain.process_device(x, first_index, out=views[slab][slot], scratch=demod)  # fused: ONE kernel; else K1 + K2
         if i is not None and not fused:
-            k1_events[i][1].record()
+            k_events[i][1].record()
         assert got.numel() == n_audio
-        if slot == GATHER_EVERY - 1 or last:
-            gather(slab, slot + 1)
-            step_no[0] += GATHER_EVERY - 1 - slot  # a partial slab at the end of a phase: start the next phase on a fresh slab
+        if slot == ge - 1 or last:
+            if gather is not None:
+                gather.submit(slab, [(slot + 1) * n_audio] * world)
+            step_no[0] += ge - 1 - slot  # a partial slab at the end of a phase: start the next phase on a fresh slab
 
-    def barrier():
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(comm_stream)
-            dist.barrier()
-        torch.cuda.synchronize()
+    def quiesce():
+        if gather is not None:
+            gather.finish()
+        ctx.barrier()
 
-    # warm-up: first the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would
-    # run different counts), then max(W, 3) complete steps including the gather, in lockstep on every rank
-    warm_steps = 0
+    # warm-up: first the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would run
+    # different counts), then max(W, 3) complete steps including the gather, in lockstep on every rank
+    # the clock sampler polls every 50 ms and the timed region of a 20-step run lasts ~2 ms: it runs from the warm-up (the same
+    # kernel back to back, the same load) through the timed region, and reports the samples taken under load
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    extra = 0
     t_warm = time.perf_counter()
     while time.perf_counter() - t_warm < args.warmup_seconds:
-        chain.process_device(x, first_index, out=slabs[0][0], scratch=demod)
-        warm_steps += 1
-        if warm_steps % 16 == 0:
+        chain.process_device(x, first_index, out=views[0][0], scratch=demod)
+        extra += 1
+        if extra % 16 == 0:
             torch.cuda.synchronize()
     n_warm = max(args.warmup, 3)
     for w in range(n_warm):
         step(last=(w == n_warm - 1))
-        warm_steps += 1
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    quiesce()
     launches0 = sdr._native.launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    t_start, t_kernels, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    quiesce()
     t_start.record()
     for i in range(args.steps):
         step(i, last=(i == args.steps - 1))
-    if world > 1:
-        torch.cuda.current_stream().wait_stream(comm_stream)  # the last gathers are part of the timed region
+    t_kernels.record()  # the last kernel of this rank
+    if gather is not None:
+        gather.finish()  # the gathers are part of the timed region
     t_end.record()
-    barrier()
+    ctx.barrier()
     launches = sdr._native.launch_count() - launches0
-    total_ms = t_start.elapsed_time(t_end)
-    # fused route: ONE kernel per step and nothing else on the stream, so the kernel's average duration is the step time
-    # (launch gaps included: an upper bound); events between the launches would serialise what programmatic dependent
-    # launch overlaps.  Two-kernel route: events around K1 + K2 of every step.
-    k1_ms = total_ms / args.steps if fused else statistics.mean(a.elapsed_time(b) for a, b in k1_events)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    my_ms, my_kernel_ms = t_start.elapsed_time(t_end), t_start.elapsed_time(t_kernels)
+    clocks = sampler.stop()
+    # fused route: ONE kernel per step and nothing else on the stream, so the kernel's average duration is the step time (launch
+    # gaps included: an upper bound); events between the launches would serialise what programmatic dependent launch overlaps.
+    # Two-kernel route: events around K1 + K2 of every step.
+    k_ms = my_kernel_ms / args.steps if fused else statistics.mean(a.elapsed_time(b) for a, b in k_events)
+    total_ms = ctx.max_over_ranks(my_ms)
+    per_rank = ctx.gather_objects({"rank": rank, "ms_per_step": my_ms / args.steps, "kernel_ms_per_step": my_kernel_ms / args.steps,
+                                   "comm_exposed_ms": my_ms - my_kernel_ms, "clocks": clocks})
+    gstats = gather.stats() if gather is not None else None
 
-    # ---- end to end: host (pinned) input -> C-ABI host call -> host output, H2D/D2H inside the timed region
+    # ---- end to end ------------------------------------------------------------------------------------------------
     e2e = None
     if not args.skip_e2e:
+        # (1) the C-ABI host call: pinned host buffers, H2D / kernel / D2H double-buffered inside b200sdr_chain_process_host
         xh = torch.empty(2 * n, dtype=torch.int8).pin_memory()
         xh.copy_(x)
         outh = torch.empty(n_audio, dtype=torch.float32).pin_memory()
         e2e_steps = max(2, min(args.steps, 5))
         chain.process_host(xh, first_index, out=outh)  # warm-up: allocates the staging slots
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             got = chain.process_host(xh, first_index, out=outh)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
         assert got.numel() == n_audio
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * n * e2e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n_audio,
-               "steps": e2e_steps, "api": "b200sdr_chain_process_host (pinned host buffers; double-buffered H2D/K1/K2/D2H)"}
+        c_abi = {"value": world * n * e2e_steps / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n_audio,
+                 "steps": e2e_steps, "api": "b200sdr_chain_process_host (C-ABI; pinned host buffers; double-buffered H2D / kernel / D2H)"}
         del xh
-    clocks = sampler.stop() if rank == 0 else None
+        # (2) the reference-facing plugin API (the headline): one fused Filter between two CudaMemcpyFilters
+        api = e2e_filter_api(ctx, wl)
+        if rank == 0:
+            if api is not None and api.get("value"):
+                e2e = dict(api)
+                e2e["c_abi"] = c_abi
+            else:
+                e2e = dict(c_abi)
+                e2e["filter_api"] = api
 
+    line = None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        peak, peak_src = hbm_peak()
         if fused:  # one kernel: 2 B/sample of int8 IQ in, 4 B per audio sample out, nothing in between
             alg_bytes = 2.0 * n + 4.0 * n_audio
             kernel_name = ("toepKernel" if chain.variant.startswith("toeplitz<") else "chainKernel") + \
@@ -417,230 +549,324 @@ def run_ours(args):
         else:      # K1 + K2: the demodulated stream makes one round trip through HBM
             alg_bytes = 2.0 * n + 8.0 * n_demod + 4.0 * n_audio
             kernel_name = "rowsKernel + directKernel (two launches per step)"
-        achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-        traffic = None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of this kernel variant (profiles/)
-            t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if chain.variant.startswith(t["variant_prefix"]) and t["samples_per_launch"] == n:
-                traffic = t["dram_bytes_per_launch"]
-        except Exception:
-            pass
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        if fused and world == 1 and not args.skip_ncu:
+            traffic = measure_traffic_with_ncu(wl, args.log2_block, chain.variant)
+            traffic_src = "measured by this run: ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch (child process)" if traffic else None
+        if traffic is None:
+            try:  # the committed ncu --set full capture of this kernel variant (profiles/)
+                t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                for entry in t if isinstance(t, list) else [t]:
+                    if chain.variant.startswith(entry["variant_prefix"]) and entry["samples_per_launch"] == n:
+                        traffic, traffic_src = entry["dram_bytes_per_launch"], "committed capture: " + entry["source"]
+            except Exception:
+                pass
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": warm_steps, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": n_warm, "warmup_extra_steps": extra, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, wl, {"kernel_variant": chain.variant}),
+            "config": config_dict(wl, args.log2_block, extra={
+                "kernel_variant": chain.variant,
+                "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
+                "parallelism": "overlapped time segments, one per GPU, no collective on the filter path; b200sdr_gather (libb200sdr.so): one "
+                               f"grouped NCCL send/recv per {ge} steps of audio to rank 0 on a side stream, 3 slabs" if world > 1 else
+                               "single GPU"}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": kernel_name, "kernel_ms": k1_ms,
+                         "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
             "gpu_launches": int(launches), "clocks": clocks,
+            "per_rank": per_rank, "comm_exposed_ms": max(p["comm_exposed_ms"] for p in per_rank),
         }
+        if gstats:
+            line["gather"] = {"steps_per_gather": ge, "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
+                              "bytes_into_rank0_per_step": 4 * n_audio * (world - 1)}
         if e2e:
             line["e2e"] = e2e
-        if not args.skip_cpu and world == 1:  # the CPU baseline is reported at N = 1 only
-            v, cores, sample, _, _ = cpu_chain_rate(wl, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        if world == 1 and not args.skip_e2e:
-            line.update(reference_api_rates(wl))
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    del x, demod, views
+    if gather is not None:
+        gather.close()
+    torch.cuda.empty_cache()
+    return line, wl
 
 
 # ---------------------------------------------------------------------------------------------------
-# C5: wideband channelizer, channels sharded over the GPUs (strong scaling: the same input on every GPU)
+# C5: wideband channelizer (strong scaling: one fixed block, split over the GPUs)
 # ---------------------------------------------------------------------------------------------------
-def run_channelizer(args):
-    import torch
-    import torch.distributed as dist
-
+def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=False):
+    """One measurement of the C5 workload.  Sharded over ctx.world GPUs, or (only_rank0_unsharded) the whole block on rank 0 alone
+    with the other ranks idle -- the N = 1 figure a speed-up is quoted against, taken in the same run."""
     import cuda_sdr_b200 as sdr
-    from cuda_sdr_b200 import sharding, taps
+    from cuda_sdr_b200 import sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.all_reduce(torch.zeros(1, device=dev))
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-
-    fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5            # 153.6 Msps = 48 kHz x 640 x 5
+    torch = ctx.torch
+    world = 1 if only_rank0_unsharded else ctx.world
+    rank = 0 if only_rank0_unsharded else ctx.rank
+    dev = ctx.dev
+    taps = load_taps_module()
+    fs, T1c, D1c, T2c, D2c = 153.6e6, 4097, 640, 273, 5            # SURVEY section 8(d): 153.6 Msps = 48 kHz x 640 x 5
     total = args.channels
-    log2n = args.log2_block if args.log2_block != LOG2_BLOCK else 29  # 3.5 s of signal per step: long segments amortise the per-launch costs at N = 8
     n = 1 << log2n
     freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]  # 600 kHz raster
     mods = [c & 1 for c in range(total)]                             # alternating AM / FM
-    t1 = taps.lowpass(T1, 100e3, fs)
-    t2 = taps.lowpass(T2, 0.45 * 48e3, fs / D1)
-    gain = sdr.fm_gain(fs / D1, 75e3)
+    t1 = taps.lowpass(T1c, 100e3, fs)
+    t2 = taps.lowpass(T2c, 0.45 * 48e3, fs / D1c)
+    gain = sdr.fm_gain(fs / D1c, 75e3)
     x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120005)           # identical on every rank: stands in for a broadcast feed
     # Two decompositions, no collective on the filter path either way (SURVEY 8(e)):
     #   filter-bank route (all channels on one raster: ONE pass yields every channel) -> overlapped TIME segments, every GPU
-    #     produces all channels for its share of the audio outputs;
+    #     produces all channels for its share of the audio outputs (b200sdr_channelizer_segment);
     #   per-channel route -> channel c on rank c mod G, input replicated.
-    probe = sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=[gain] * total, device=local_rank)
-    by_time = probe.variant.startswith("pfb<") and args.shard != "channels"
+    probe = sdr.Channelizer(fs, freqs, mods, t1, D1c, t2, D2c, fm_gains=[gain] * total, device=ctx.local_rank)
+    by_time = probe.variant.startswith("pfb") and args.shard != "channels"
     if by_time:
         mine = list(range(total))
         ch = probe
         _, n_audio_total = ch.counts(n)
-        window = sharding.chain_window(T1, D1, T2, any(mods), True)
-        seg = sharding.time_segment(n_audio_total, world, rank, D1 * D2, window)
-        x_mine = x[2 * seg.first_input: 2 * (seg.first_input + seg.input_count)]
-        n_audio = seg.output_count
-        counts_audio = [sharding.time_segment(n_audio_total, world, r, D1 * D2, window).output_count for r in range(world)]
-        shapes = [(total, counts_audio[r]) for r in range(world)]
+        segs = [ch.segment(n_audio_total, world, r) for r in range(world)]
+        first_out, n_audio, first_in, in_count = segs[rank]
+        x_mine = x[2 * first_in: 2 * (first_in + in_count)]
+        floats = [total * s[1] for s in segs]
     else:
         mine = sharding.channels_of_rank(total, world, rank)
-        ch = sdr.Channelizer(fs, [freqs[c] for c in mine], [mods[c] for c in mine], t1, D1, t2, D2, fm_gains=[gain] * len(mine), device=local_rank)
+        ch = sdr.Channelizer(fs, [freqs[c] for c in mine], [mods[c] for c in mine], t1, D1c, t2, D2c, fm_gains=[gain] * len(mine),
+                             device=ctx.local_rank)
         del probe
         x_mine = x
         _, n_audio = ch.counts(n)
-        shapes = [(len(sharding.channels_of_rank(total, world, r)), n_audio) for r in range(world)]
-    n_demod = (n_audio - 1) * D2 + T2
+        floats = [len(sharding.channels_of_rank(total, world, r)) * n_audio for r in range(world)]
+    n_demod = (n_audio - 1) * D2c + T2c
     scratch = torch.empty(len(mine), n_demod, dtype=torch.float32, device=dev)
-    outs = [torch.empty(len(mine), n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
-    gathered = [[torch.empty(*shapes[r], dtype=torch.float32, device=dev) for r in range(world)] for _ in range(2)] \
-        if (world > 1 and rank == 0) else None
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    done_evt = [torch.cuda.Event() for _ in range(2)]
-    drained = [torch.cuda.Event() for _ in range(2)]
-    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    slabs = 3
+    gather = ctx.make_gather(floats, slabs) if world > 1 else None
+    if gather is not None:
+        outs = [gather.slab(s)[: len(mine) * n_audio].view(len(mine), n_audio) for s in range(slabs)]
+    else:
+        outs = [torch.empty(len(mine), n_audio, dtype=torch.float32, device=dev) for _ in range(2)]
+    k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     step_no = [0]
 
     def step(i=None):
-        buf = step_no[0] & 1
+        buf = step_no[0] % len(outs)
         step_no[0] += 1
-        if world > 1:
-            torch.cuda.current_stream().wait_event(drained[buf])
+        if gather is not None:
+            gather.acquire(buf)
         if i is not None:
             k_events[i][0].record()
         ch.run(x_mine, n_audio, out=outs[buf], scratch=scratch)
         if i is not None:
             k_events[i][1].record()
-        if world > 1:  # gather this step's audio of every rank's channels to rank 0 on the side stream
-            done_evt[buf].record()
-            with torch.cuda.stream(comm):
-                comm.wait_event(done_evt[buf])
-                if rank == 0:
-                    gathered[buf][0].copy_(outs[buf], non_blocking=True)
-                    ops = [dist.P2POp(dist.irecv, gathered[buf][r], r) for r in range(1, world)]
-                else:
-                    ops = [dist.P2POp(dist.isend, outs[buf], 0)]
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-                drained[buf].record()
+        if gather is not None:  # this step's audio of every rank to rank 0 on the side stream
+            gather.submit(buf)
 
-    def barrier():
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(comm)
-            dist.barrier()
-        torch.cuda.synchronize()
+    def quiesce():
+        if gather is not None:
+            gather.finish()
+        if only_rank0_unsharded:
+            torch.cuda.synchronize()
+        else:
+            ctx.barrier()
 
     t_warm = time.perf_counter()
-    warm = 0
-    while time.perf_counter() - t_warm < args.warmup_seconds:
+    extra = 0
+    while time.perf_counter() - t_warm < min(args.warmup_seconds, 0.3):
         ch.run(x_mine, n_audio, out=outs[0], scratch=scratch)
-        warm += 1
+        extra += 1
         torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(warmup, 3)
+    for _ in range(n_warm):
         step()
-        warm += 1
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    quiesce()
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
     launches0 = sdr._native.launch_count()
-    t0, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    t0, tk, t1e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    quiesce()
     t0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
-    if world > 1:
-        torch.cuda.current_stream().wait_stream(comm)
+    tk.record()
+    if gather is not None:
+        gather.finish()
     t1e.record()
-    barrier()
+    quiesce()
     launches = sdr._native.launch_count() - launches0
-    total_ms = t0.elapsed_time(t1e)
+    my_ms, my_kernel_ms = t0.elapsed_time(t1e), t0.elapsed_time(tk)
     k_ms = statistics.mean(a.elapsed_time(b) for a, b in k_events)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if only_rank0_unsharded:
+        total_ms, per_rank = my_ms, None
+    else:
+        total_ms = ctx.max_over_ranks(my_ms)
+        per_rank = ctx.gather_objects({"rank": rank, "ms_per_step": my_ms / steps, "kernel_ms_per_step": my_kernel_ms / steps,
+                                       "comm_exposed_ms": my_ms - my_kernel_ms, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons")})
+    rec = None
     if rank == 0:
+        hbm, _ = hbm_peak()
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        peak = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1590.0
-        M = -(-T1 // D1)
-        pfb = ch.variant.startswith("pfb<")
+        peak_tc = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1590.0
+        M = -(-T1c // D1c)
+        pfb = ch.variant.startswith("pfb")
+        fused_audio = "audio FIR fused" in ch.variant
         samples_this_gpu = x_mine.numel() // 2
         # SURVEY 8(d): the per-channel chain costs ~38 flop per input sample per channel; the filter bank does the same job
         # for all channels at once, so the per-channel figure stays the ALGORITHMIC work the line is normalised by
-        flops = samples_this_gpu * len(mine) * (12.0 + 4.0 * T1 / D1 + 10.0 / D1 + 2.0 * T2 / (D1 * D2))
-        hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+        flops = samples_this_gpu * len(mine) * (12.0 + 4.0 * T1c / D1c + 10.0 / D1c + 2.0 * T2c / (D1c * D2c))
         if pfb:
-            # bytes the two launches must move: int8 IQ in, demodulated samples out and back in, audio out
-            alg_bytes = 2.0 * samples_this_gpu + len(mine) * (8.0 * n_demod + 4.0 * n_audio)
-            roofline = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                        "kernel": "pfbKernel (polyphase filter bank + fp64 FFT + demod, all channels) + batched audio FIR (windowKernel)",
+            # bytes the launches must move: int8 IQ in, (unless fused) demodulated samples out and back in, audio out
+            alg_bytes = 2.0 * samples_this_gpu + len(mine) * ((0.0 if fused_audio else 8.0 * n_demod) + 4.0 * n_audio)
+            roofline = {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                        "kernel": "polyphase filter bank + fp64 FFT + demod, all channels (pfb kernel) + batched audio FIR",
                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                         "per_channel_equivalent_tflops": flops / (k_ms * 1e-3) / 1e12,
-                        "note": "the filter bank replaces ~38 flop per sample PER CHANNEL by ~60 flop per sample for all channels, so the "
-                                "binding roof is HBM (2 B per sample in + the demodulated streams); today the kernel is bound by FP64 "
-                                "latency at 8 warps per SM (DESIGN.md)"}
+                        "fp64_dfma_per_step": samples_this_gpu / D1c * (4.0 * 17 * 256 + 5500.0),
+                        "note": "the filter bank replaces ~38 flop per sample PER CHANNEL by ~60 flop per sample for all channels; the binding "
+                                "unit of the kernel is the FP64 pipe (filter bank + FFT in fp64, DESIGN.md), HBM is the contract's roof"}
         else:
-            executed_ops = 2.0 * (n_demod + M) * (2 * D1) * (16 if M > 4 else 8) * 3 * len(mine)      # int8 MMA ops incl. digits and padding
-            roofline = {"bound": "tensor", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                        "frac": flops / (k_ms * 1e-3) / 1e12 / peak, "traffic": None,
+            executed_ops = 2.0 * (n_demod + M) * (2 * D1c) * (16 if M > 4 else 8) * 3 * len(mine)      # int8 MMA ops incl. digits and padding
+            roofline = {"bound": "tensor", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak_tc, "unit": "TFLOP/s",
+                        "frac": flops / (k_ms * 1e-3) / 1e12 / peak_tc, "traffic": None,
                         "kernel": "channelKernel (int8 GEMM RF stage + demod) + batched audio FIR", "kernel_ms": k_ms,
                         "algorithmic_flops_per_launch": flops, "executed_int8_tops": executed_ops / (k_ms * 1e-3) / 1e12,
-                        "legacy_imma_peak_tops_measured": 1143.0,
-                        "note": "algorithmic flops (SURVEY 8(d): ~38 per sample per channel) against the measured bf16 GEMM peak; the kernel "
-                                "executes the contraction as 3 int8 digit MMAs on the legacy IMMA path (tools/imma_bench.cu: 1143 TOP/s on this part)"}
-        line = {
+                        "legacy_imma_peak_tops_measured": 1143.0}
+        rec = {
             "metric": "input Msps through the 256-channel wideband channelizer (int8 -> mix -> FIR -> AM/FM demod -> audio FIR per channel)",
-            "value": n * args.steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "value": n * steps / (total_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": n_warm, "warmup_extra_steps": extra,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 filter bank + FFT, f32 demod / audio FIR" if pfb else "s8 x s8 -> s32 (24-bit fixed-point taps), f32 epilogue",
             "data": "synthetic",
             "config": {"workload": f"C5 wideband channelizer: 2^{log2n} int8 IQ samples per step at 153.6 Msps-class rate, {total} channels on a 600 kHz "
-                                   f"raster alternating AM/FM, per channel mix -> {T1}-tap FIR /{D1} -> demod -> {T2}-tap audio FIR /{D2}",
+                                   f"raster alternating AM/FM, per channel mix -> {T1c}-tap FIR /{D1c} -> demod -> {T2c}-tap audio FIR /{D2c}",
                        "channels_total": total, "channels_this_gpu": len(mine), "samples_per_step": n, "samples_this_gpu": samples_this_gpu,
-                       "parallelism": ("overlapped time segments of the wideband stream, every GPU produces all channels for its share of the audio outputs"
-                                       if by_time else "channels interleaved over the GPUs (c mod G), input replicated") +
-                                      "; NCCL send/recv gather of the audio to rank 0 on a side stream",
-                       "l2": f"input block {2 * n >> 20} MiB exceeds the 126 MB L2", "kernel_variant": ch.variant},
-            "roofline": roofline,
-            "gpu_launches": int(launches), "clocks": clocks,
+                       "route": ch.variant,
+                       "parallelism": (("overlapped time segments of the wideband stream, every GPU produces all channels for its share of the "
+                                        "audio outputs" if by_time else "channels interleaved over the GPUs (c mod G), input replicated") +
+                                       "; b200sdr_gather: one grouped NCCL send/recv per step of audio to rank 0 on a side stream, 3 slabs")
+                       if world > 1 else "single GPU",
+                       "l2": f"input block {2 * n >> 20} MiB exceeds the 126 MB L2"},
+            "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        if per_rank is not None and world > 1:
+            rec["per_rank"] = per_rank
+            rec["comm_exposed_ms"] = max(p["comm_exposed_ms"] for p in per_rank)
+            rec["gather"] = {"bytes_into_rank0_per_step": 4 * sum(floats[1:]), "slabs": slabs, "calls": gather.stats()["gathers"]}
+    del x, x_mine, scratch, outs
+    if gather is not None:
+        gather.close()
+    ch.close()
+    torch.cuda.empty_cache()
+    return rec
+
+
+def channelizer_record(args, ctx, steps, warmup, log2n):
+    """C5 on ctx.world GPUs plus, for N > 1, the same block on ONE GPU in the same run (rank 0 alone, the others wait)."""
+    rec = measure_channelizer(args, ctx, steps, warmup, log2n)
+    if ctx.world > 1:
+        single = measure_channelizer(args, ctx, max(3, steps // 2), warmup, log2n, only_rank0_unsharded=True) if ctx.rank == 0 else None
+        ctx.barrier()
+        if ctx.rank == 0:
+            rec["single_gpu_same_run"] = {"value": single["value"], "ms_per_step": single["ms_per_step"], "unit": UNIT, "steps": single["steps"]}
+            rec["speedup_vs_single_gpu_same_run"] = rec["value"] / single["value"]
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------
+# C4: FIR roofline sweep through the gsdr C-ABI (gsdrFirFC), one GPU
+# ---------------------------------------------------------------------------------------------------
+def run_firsweep(args, ctx):
+    import cuda_sdr_b200 as sdr
+    from cuda_sdr_b200 import ops
+
+    torch = ctx.torch
+    if ctx.rank != 0:
+        return None
+    taps = load_taps_module()
+    hbm, peak_src = hbm_peak()
+    ffma = 71.0  # TFLOP/s, tools/microbench.cu (ffma_rrr) on this pool's B200 at 1.965 GHz
+    log2 = args.log2_block if args.log2_block != LOG2_BLOCK else 26
+    n = 1 << log2
+    x = torch.view_as_complex(torch.randn(n, 2, device=ctx.dev, dtype=torch.float32))
+    cells, launches0 = [], sdr._native.launch_count()
+    reps = max(1, min(args.steps, 5))
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    t_all0 = time.perf_counter()
+    for T in [32, 64, 128, 256, 512, 1024, 2048, 4096]:
+        h = torch.from_numpy(taps.lowpass(T, 0.2, 1.0)).to(ctx.dev)
+        for D in [1, 2, 4, 8, 16, 32, 64]:
+            n_out = ops.fir_num_outputs(n, T, D)
+            for _ in range(max(1, min(args.warmup, 2))):
+                ops.fir("fc", h, x, D, n_out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            times, spent = [], 0.0
+            while len(times) < reps and (spent < 400.0 or not times):
+                e0.record()
+                ops.fir("fc", h, x, D, n_out)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+                spent += times[-1]
+            ms = statistics.median(times)
+            gbs = n * (8.0 + 8.0 / D) / (ms * 1e-3) / 1e9
+            tflops = n * 4.0 * T / D / (ms * 1e-3) / 1e12
+            t_roof = max(n * (8.0 + 8.0 / D) / (hbm * 1e9), n * 4.0 * T / D / (ffma * 1e12)) * 1e3
+            cells.append({"taps": T, "decimation": D, "ms": ms, "msps": n / (ms * 1e-3) / 1e6, "gbs": gbs, "tflops": tflops,
+                          "bound": "hbm" if gbs / hbm >= tflops / ffma else "ffma", "frac": t_roof / ms})
+    wall = time.perf_counter() - t_all0
+    clocks = sampler.stop()
+    fracs = [c["frac"] for c in cells]
+    total_samples = n * len(cells)
+    total_ms = sum(c["ms"] for c in cells)
+    worst = min(cells, key=lambda c: c["frac"])
+    return {
+        "metric": "input Msps of the decimating FIR (gsdrFirFC: real taps x complex float), mean over the C4 sweep cells", "value": total_samples / (total_ms * 1e-3) / 1e6,
+        "unit": UNIT, "n_gpus": 1, "steps": reps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": total_ms / len(cells), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C4 FIR roofline sweep: T in 32..4096 x D in 1..64 on 2^{log2} complex-float samples (512 MiB > L2), one B200, "
+                               "through the gsdr C-ABI", "cells": len(cells), "wall_seconds": wall},
+        "roofline": {"bound": worst["bound"], "achieved": worst["gbs"] if worst["bound"] == "hbm" else worst["tflops"],
+                     "peak": hbm if worst["bound"] == "hbm" else ffma, "unit": "GB/s" if worst["bound"] == "hbm" else "TFLOP/s",
+                     "frac": worst["frac"], "traffic": None, "kernel": f"worst cell: T={worst['taps']} D={worst['decimation']}",
+                     "frac_min": min(fracs), "frac_median": statistics.median(fracs), "frac_max": max(fracs),
+                     "cells_at_or_above_0.70": sum(f >= 0.70 for f in fracs), "peak_source": peak_src + "; FFMA 71 TFLOP/s measured (tools/microbench.cu)"},
+        "cells": cells, "gpu_launches": int(sdr._native.launch_count() - launches0), "clocks": clocks,
+    }
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    if args.workload == "channelizer":
-        return run_channelizer(args)
-    return run_ours(args)
+    ctx = Ctx(args)
+    line = None
+    if args.workload == "firsweep":
+        line = run_firsweep(args, ctx)
+    elif args.workload == "channelizer":
+        log2n = args.log2_block if args.log2_block != LOG2_BLOCK else 29  # 3.5 s of signal per step: long segments amortise per-launch costs at N = 8
+        line = channelizer_record(args, ctx, args.steps, args.warmup, log2n)
+    else:
+        line, wl = run_chain(args, ctx)
+        if not args.skip_channelizer:
+            # the north-star scaling workload rides on every line: C5, 256 channels, the same N GPUs, strong scaling
+            sub = channelizer_record(args, ctx, max(5, min(args.steps, 20)), 3, 29)
+            if ctx.rank == 0:
+                keep = ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "single_gpu_same_run", "speedup_vs_single_gpu_same_run",
+                        "comm_exposed_ms", "gather", "per_rank", "gpu_launches")
+                line["channelizer"] = {k: sub[k] for k in keep if k in sub}
+                line["channelizer"]["route"] = sub["config"]["route"]
+                line["channelizer"]["workload"] = sub["config"]["workload"]
+                line["channelizer"]["roofline_frac"] = sub["roofline"]["frac"]
+        if ctx.rank == 0 and not args.skip_cpu and ctx.world == 1:  # the CPU baseline is reported at N = 1 only
+            v, cores, sample = cpu_chain_rate(wl, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if ctx.rank == 0 and ctx.world == 1 and not args.skip_e2e:
+            line.update(reference_pipeline_rate(wl))
+    if ctx.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    return 0
 
 
 if __name__ == "__main__":

@@ -66,6 +66,15 @@ class ChannelizerConfig(C.Structure):
     ]
 
 
+class GatherConfig(C.Structure):
+    """Mirror of b200sdr_gather_config (include/b200sdr/b200sdr.h)."""
+
+    _fields_ = [
+        ("struct_size", u32), ("rank", i32), ("world", i32), ("slabs", u32), ("cuda_device", i32),
+        ("floats_per_rank", C.POINTER(sz)), ("nccl_unique_id", vp),
+    ]
+
+
 psz = C.POINTER(sz)
 B200SDR_SYMBOLS = {
     "b200sdr_chain_create": (u32, [C.POINTER(ChainConfig), C.POINTER(vp)]),
@@ -91,6 +100,16 @@ B200SDR_SYMBOLS = {
     "b200sdr_channelizer_process": (u32, [vp, vp, sz, vp, sz, vp, sz, psz, stream_t]),
     "b200sdr_channelizer_variant": (C.c_char_p, [vp]),
     "b200sdr_channelizer_raster": (u32, [C.POINTER(f64), u32, f64, C.POINTER(i32)]),
+    "b200sdr_channelizer_segment": (u32, [vp, sz, sz, sz, psz, psz, psz, psz]),
+    "b200sdr_nccl_unique_id": (u32, [vp]),
+    "b200sdr_gather_create": (u32, [C.POINTER(GatherConfig), C.POINTER(vp)]),
+    "b200sdr_gather_destroy": (None, [vp]),
+    "b200sdr_gather_slab": (vp, [vp, u32]),
+    "b200sdr_gather_acquire": (u32, [vp, u32, stream_t]),
+    "b200sdr_gather_submit": (u32, [vp, u32, psz, stream_t]),
+    "b200sdr_gather_finish": (u32, [vp, stream_t]),
+    "b200sdr_gather_result": (vp, [vp, u32, i32]),
+    "b200sdr_gather_stats": (None, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]),
     "b200sdr_launch_count": (u64, []),
     "b200sdr_chain_variant": (C.c_char_p, [vp]),
     "b200sdr_version": (C.c_char_p, []),

@@ -63,6 +63,13 @@ class Channelizer:
         _lib.b200sdr_channelizer_counts(self._h, n_in, C.byref(demod), C.byref(audio))
         return demod.value, audio.value
 
+    def segment(self, num_audio: int, parts: int, index: int):
+        """(first_output, output_count, first_input, input_count) of time-segment `index` of `parts` (all channels per segment)."""
+        v = [C.c_size_t() for _ in range(4)]
+        N.check_status(_lib.b200sdr_channelizer_segment(self._h, num_audio, parts, index, *[C.byref(x) for x in v]),
+                       "b200sdr_channelizer_segment")
+        return tuple(x.value for x in v)
+
     def channel_counts(self, channel: int, n_in: int):
         """(demod, audio) counts of one channel by the reference's per-node rules (an AM channel keeps its own count)."""
         demod, audio = C.c_size_t(), C.c_size_t()

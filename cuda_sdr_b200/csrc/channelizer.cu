@@ -325,6 +325,21 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_channel_counts(
   return B200SDR_OK;
 }
 
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_segment(
+    const b200sdr_channelizer* c, size_t numAudio, size_t parts, size_t index, size_t* firstOutput, size_t* outputCount, size_t* firstInput,
+    size_t* inputCount) {
+  if (!c || parts == 0 || index >= parts) return chainFail(B200SDR_INVALID_ARGUMENT, "bad segment request");
+  const size_t base = numAudio / parts, extra = numAudio % parts;
+  const size_t first = index * base + (index < extra ? index : extra), count = base + (index < extra ? 1 : 0);
+  const size_t stride = static_cast<size_t>(c->D1) * c->D2;
+  const size_t window = (static_cast<size_t>(c->T2) - 1 + (c->anyFm ? 1 : 0)) * c->D1 + c->T1;  // RF taps + the demod samples of one audio window
+  if (firstOutput) *firstOutput = first;
+  if (outputCount) *outputCount = count;
+  if (firstInput) *firstInput = first * stride;
+  if (inputCount) *inputCount = count == 0 ? 0 : (count - 1) * stride + window;
+  return B200SDR_OK;
+}
+
 namespace {
 
 // the AM channels' rows of tail[] -> column `col` of audio (one thread per channel)

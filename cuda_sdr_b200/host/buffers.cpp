@@ -501,10 +501,13 @@ Result<IBuffer> newBufferSlice(IBuffer* parent, size_t start, size_t end) noexce
   UNWRAP_OR_FWD_RESULT(range, newBufferRange());
   range.get()->setCapacity(end - start);
   const size_t pOff = parent->range()->offset(), pEnd = parent->range()->endOffset();
-  auto clampTo = [&](size_t v) { return v < pOff ? pOff : v > pEnd ? pEnd : v; };
-  if (!(start < pOff && end < pOff)) {
-    FWD_IN_RESULT_IF_ERR(range.get()->setUsedRange(clampTo(start) - start, clampTo(end) - start));
-  }
+  // the slice's used range = the parent's used range seen through the window [start, end), relative to `start`
+  // (reference BufferSlice.cpp:24-42): empty at 0 when the window lies behind the parent's data, empty at the window's
+  // end when it lies in front of it
+  const size_t len = end - start;
+  const size_t sOff = pOff <= start ? 0 : pOff >= end ? len : pOff - start;
+  const size_t sEnd = pEnd >= end ? len : pEnd <= start ? 0 : pEnd - start;
+  FWD_IN_RESULT_IF_ERR(range.get()->setUsedRange(sOff < sEnd ? sOff : sEnd, sEnd));
   return makeRefResultNonNull<IBuffer>(new (std::nothrow) SliceBuffer(parent, start, range.get()));
 }
 

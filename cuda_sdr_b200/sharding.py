@@ -67,3 +67,89 @@ def gather_to_rank0(local, counts: list[int], group=None):
     if counts[rank]:
         dist.send(local.contiguous(), dst=0, group=group)
     return None
+
+
+class _DevicePointer:
+    """A raw device pointer presented through the CUDA array interface, so that torch can view library-owned memory."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class Gather:
+    """ctypes front-end of b200sdr_gather (include/b200sdr/b200sdr.h): the gather of every rank's decimated audio to
+    rank 0 over NCCL, slab by slab on a side stream.  The communicator, the slabs, the events and the grouped send/recv
+    live in libb200sdr.so; the caller only distributes the 128-byte NCCL unique id (`unique_id()` on rank 0)."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        import ctypes as C
+        from . import _native as N
+        buf = C.create_string_buffer(128)
+        N.check_status(N.lib.b200sdr_nccl_unique_id(buf), "b200sdr_nccl_unique_id")
+        return buf.raw
+
+    def __init__(self, rank: int, world: int, floats_per_rank, slabs: int = 3, device: int = 0, unique_id: bytes | None = None):
+        import ctypes as C
+        from . import _native as N
+        self._N, self._C = N, C
+        self.rank, self.world, self.slabs, self.device = rank, world, slabs, device
+        self.floats_per_rank = [int(v) for v in floats_per_rank]
+        assert len(self.floats_per_rank) == world
+        self._counts = (C.c_size_t * world)(*self.floats_per_rank)
+        self._id = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        cfg = N.GatherConfig()
+        cfg.struct_size = C.sizeof(N.GatherConfig)
+        cfg.rank, cfg.world, cfg.slabs, cfg.cuda_device = rank, world, slabs, device
+        cfg.floats_per_rank = self._counts
+        cfg.nccl_unique_id = C.cast(self._id, C.c_void_p) if self._id is not None else None
+        handle = C.c_void_p()
+        N.check_status(N.lib.b200sdr_gather_create(C.byref(cfg), C.byref(handle)), "b200sdr_gather_create")
+        self._h = handle
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._N.lib.b200sdr_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def slab(self, index: int):
+        """This rank's part of slab `index` as a 1-D float32 torch tensor (a view of library-owned device memory)."""
+        import torch
+        ptr = self._N.lib.b200sdr_gather_slab(self._h, index)
+        return torch.as_tensor(_DevicePointer(ptr, max(self.floats_per_rank[self.rank], 1)), device=torch.device("cuda", self.device))
+
+    def result(self, index: int, rank: int):
+        """Rank 0: rank `rank`'s part of gathered slab `index` (valid in stream order after finish())."""
+        import torch
+        ptr = self._N.lib.b200sdr_gather_result(self._h, index, rank)
+        if not ptr:
+            return None
+        return torch.as_tensor(_DevicePointer(ptr, max(self.floats_per_rank[rank], 1)), device=torch.device("cuda", self.device))
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+
+    def acquire(self, index: int):
+        self._N.check_status(self._N.lib.b200sdr_gather_acquire(self._h, index, self._stream()), "b200sdr_gather_acquire")
+
+    def submit(self, index: int, floats_per_rank=None):
+        counts = None
+        if floats_per_rank is not None:
+            counts = (self._C.c_size_t * self.world)(*[int(v) for v in floats_per_rank])
+        self._N.check_status(self._N.lib.b200sdr_gather_submit(self._h, index, counts, self._stream()), "b200sdr_gather_submit")
+
+    def finish(self):
+        self._N.check_status(self._N.lib.b200sdr_gather_finish(self._h, self._stream()), "b200sdr_gather_finish")
+
+    def stats(self):
+        C = self._C
+        gathers, moved, version = C.c_uint64(), C.c_uint64(), C.c_int32()
+        self._N.lib.b200sdr_gather_stats(self._h, C.byref(gathers), C.byref(moved), C.byref(version))
+        return {"gathers": gathers.value, "floats_moved": moved.value, "nccl_version": version.value}

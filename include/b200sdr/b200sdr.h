@@ -179,6 +179,44 @@ B200SDR_EXPORT const char* b200sdr_channelizer_variant(const b200sdr_channelizer
    still pick a finer raster if the tables of the coarsest do not fit in shared memory).  Needs no GPU. */
 B200SDR_EXPORT uint32_t b200sdr_channelizer_raster(const double* frequencies, uint32_t numChannels, double sampleRate, int32_t* bins);
 
+/* Time-segment sharding of the channelizer (the filter-bank route yields every channel from one pass, so GPUs split the
+ * audio outputs, not the channels): part `index` of `parts` of numAudio outputs per channel -- first output, count, first
+ * input sample and number of input samples it reads (look-ahead halo included).  As b200sdr_chain_segment. */
+B200SDR_EXPORT b200sdr_status b200sdr_channelizer_segment(
+    const b200sdr_channelizer* channelizer, size_t numAudio, size_t parts, size_t index, size_t* firstOutput, size_t* outputCount,
+    size_t* firstInput, size_t* inputCount);
+
+/* ---- multi-GPU: the gather of decimated audio to rank 0 (the ONLY exchange of the sharded path) ------------------- */
+/* One rank per GPU (one process per GPU, or one host thread per GPU).  Every rank runs its own time segment
+ * (b200sdr_chain_segment / b200sdr_channelizer_segment) or its own channels -- no collective on the filter path
+ * (reference: none; src/commandqueue/CommandQueueFactory.cpp:59-62 only lets a queue name a device).  The audio is
+ * written into a slab of this object and gathered to rank 0 with one grouped NCCL send/recv per slab on a side stream,
+ * overlapping the kernels of the next steps.  NCCL is loaded at run time (libnccl.so.2); world == 1 needs none. */
+typedef struct b200sdr_gather_config {
+  uint32_t struct_size;
+  int32_t rank, world;
+  uint32_t slabs;                 /* >= 2; 3 lets the main stream run ahead while two gathers drain */
+  int32_t cuda_device;
+  const size_t* floats_per_rank;  /* HOST, `world` entries: capacity of each rank's part of one slab, in floats */
+  const void* nccl_unique_id;     /* 128 bytes made by b200sdr_nccl_unique_id() on rank 0 and handed to every rank by the caller */
+} b200sdr_gather_config;
+typedef struct b200sdr_gather b200sdr_gather;
+B200SDR_EXPORT b200sdr_status b200sdr_nccl_unique_id(void* id128);
+B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config* config, b200sdr_gather** out);
+B200SDR_EXPORT void b200sdr_gather_destroy(b200sdr_gather* gather);
+/* DEVICE pointer of this rank's part of slab `slab` (floats_per_rank[rank] floats): the kernels write their audio here. */
+B200SDR_EXPORT float* b200sdr_gather_slab(b200sdr_gather* gather, uint32_t slab);
+/* Before writing into a slab again: `stream` waits until the slab's previous gather has read it. */
+B200SDR_EXPORT b200sdr_status b200sdr_gather_acquire(b200sdr_gather* gather, uint32_t slab, cudaStream_t stream);
+/* After the work that fills the slab was enqueued on `stream`: gather it on the side stream.  floatsPerRank (HOST, `world`
+ * entries, identical on every rank; NULL = the capacities) gives what each rank really sends. */
+B200SDR_EXPORT b200sdr_status b200sdr_gather_submit(b200sdr_gather* gather, uint32_t slab, const size_t* floatsPerRank, cudaStream_t stream);
+/* `stream` waits for every gather submitted so far. */
+B200SDR_EXPORT b200sdr_status b200sdr_gather_finish(b200sdr_gather* gather, cudaStream_t stream);
+/* Rank 0: DEVICE pointer of rank `rank`'s part of gathered slab `slab` (valid once the gather has run); NULL elsewhere. */
+B200SDR_EXPORT const float* b200sdr_gather_result(const b200sdr_gather* gather, uint32_t slab, int32_t rank);
+B200SDR_EXPORT void b200sdr_gather_stats(const b200sdr_gather* gather, uint64_t* gathers, uint64_t* floatsMoved, int32_t* ncclVersion);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* Kernels launched by this library since load (all streams); used by bench.py's gpu_launches. */
 B200SDR_EXPORT uint64_t b200sdr_launch_count(void);

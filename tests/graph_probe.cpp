@@ -9,6 +9,7 @@
 //   --mode component   the same, with the RF-to-audio part built by createFilter("Component", json) in the reference's
 //                      schema (FilterDriverFactory.cpp:27-179) -- the exposed input port is mapped onto Multiply port 1 and
 //                      the cosine onto port 0 (a NON-identity mapping), the output through a PortRemappingSource
+//                      (--input cf32: complex-float samples from the host, no Int8ToFloat node)
 //   --mode elementwise host cf32 -> H2D -> PassThrough (an out-of-tree filter derived from BaseFilter) ->
 //                      AddConstToVectorLength -> Magnitude -> AddConst -> monitor(D2H) -> host
 // Prints one JSON line; --chunks FILE receives the element count of every cosine readOutput (the reference's float32
@@ -222,7 +223,7 @@ static int memcpyMode(IFactories* f, ICudaCommandQueue* queue) {
 }
 
 struct Args {
-  string mode = "stepping", in, out, taps1, taps2, mod = "am", dot, chunks;
+  string mode = "stepping", in, out, taps1, taps2, mod = "am", dot, chunks, input = "int8";
   double fs = 19.2e6, freq = 0, dev = 75e3, addMag = 0.25, addConst = -0.125;
   size_t d1 = 1, d2 = 1, chunk = 262144;
 };
@@ -250,6 +251,7 @@ int main(int argc, char** argv) {
     else if (k == "--mod") a.mod = v;
     else if (k == "--dot") a.dot = v;
     else if (k == "--chunks") a.chunks = v;
+    else if (k == "--input") a.input = v;
     else if (k == "--fs") a.fs = atof(v.c_str());
     else if (k == "--freq") a.freq = atof(v.c_str());
     else if (k == "--dev") a.dev = atof(v.c_str());
@@ -290,10 +292,16 @@ int main(int argc, char** argv) {
   Ref<Filter> middle;
   size_t outElemBytes = 4;
   if (chainMode) {
-    ConstRef<Filter> int8ToFloat = unwrap(f->getInt8ToFloatFactory()->createFilter(queue));
-    THROW_IF_ERR(inputPipeline->connect(h2d, 0, int8ToFloat, 0));
-    THROW_IF_ERR(inputPipeline->setupNode(int8ToFloat, "Convert complex int8 to complex float"));
-    inputPipeline->setDriverOutput(int8ToFloat);
+    if (a.input == "int8") {
+      ConstRef<Filter> int8ToFloat = unwrap(f->getInt8ToFloatFactory()->createFilter(queue));
+      THROW_IF_ERR(inputPipeline->connect(h2d, 0, int8ToFloat, 0));
+      THROW_IF_ERR(inputPipeline->setupNode(int8ToFloat, "Convert complex int8 to complex float"));
+      inputPipeline->setDriverOutput(int8ToFloat);
+    } else {
+      // complex-float samples straight from the host.  (The reference's own Int8ToFloat rejects the one-port readOutput its
+      // SteppingDriver issues -- Int8ToFloat.cpp:81 tests `0 == portCount` -- so the reference framework is driven this way.)
+      inputPipeline->setDriverOutput(h2d);
+    }
     if (a.mode == "stepping") {
       // frequency shifter: a FilterDriver whose input is a PortRemappingSink exposing Multiply port 0 (am_test.cpp:295-350)
       ConstRef<Source> cosineRaw = unwrap(f->getCosineSourceFactory()->createCosineSource(SampleType_FloatComplex, rfRate, static_cast<float>(a.freq), queue));
@@ -371,7 +379,7 @@ int main(int argc, char** argv) {
   ConstRef<IReadByteCountMonitor> monitor = unwrap(f->getReadByteCountMonitorFactory()->create(d2h));
   ConstRef<IAllocator> pinned = unwrap(f->getCudaAllocatorFactory()->createCudaAllocator(queue, 32, true));
   ConstRef<IBufferFactory> pinnedBuffers = unwrap(f->createBufferFactory(pinned));
-  const size_t inElems = chainMode ? input.size() / 2 : input.size() / 8;
+  const size_t inElems = chainMode && a.input == "int8" ? input.size() / 2 : input.size() / 8;
   ConstRef<IBuffer> storage = unwrap(pinnedBuffers->createBuffer((chainMode ? inElems / (a.d1 * a.d2) : inElems) * outElemBytes + (4 << 20)));
   ConstRef<HostSink> hostSink(new HostSink(storage, f->getBufferSliceFactory()));
   Ref<IFilterDriver> outputPipeline = unwrap(f->getFilterDriverFactory()->createFilterDriver());

@@ -70,11 +70,11 @@ def chain_args(tmp_path, mod):
             "--mod", mod, "--dev", repr(DEV), "--d1", D1, "--d2", D2]
 
 
-def cascade_oracle_ref_f32(x, chunks, t1, t2, mod):
+def cascade_oracle_ref_f32(x, chunks, t1, t2, mod, cf32=False):
     """The five-node cascade op by op in the oracle, float32 storage between nodes (every node writes cuComplex / float),
     the local oscillator generated chunk by chunk with the reference's float32 phase bookkeeping."""
     f32 = np.float32
-    n = x.size // 2
+    n = x.size if cf32 else x.size // 2
     delta = f32(2.0 * np.pi * float(f32(FREQ)) / float(f32(FS)))  # CosineSource.cpp:51: float(2 pi f / fs), f and fs are floats
     two_pi = f32(2.0) * f32(np.pi)
     phi, lo = f32(0.0), []
@@ -88,8 +88,11 @@ def cascade_oracle_ref_f32(x, chunks, t1, t2, mod):
         have += c
     lo = np.concatenate(lo)[:n].astype(np.complex64)
     assert lo.size == n, "the cosine source produced fewer samples than the input"
-    z = orc.int8_to_norm_float(x)
-    z = (z[0::2] + 1j * z[1::2]).astype(np.complex64)
+    if cf32:
+        z = np.ascontiguousarray(x, dtype=np.complex64)
+    else:
+        z = orc.int8_to_norm_float(x)
+        z = (z[0::2] + 1j * z[1::2]).astype(np.complex64)
     mixed = orc.multiply_cc(z, lo).astype(np.complex64)
     rf = orc.fir("fc", t1, mixed, D1).astype(np.complex64)
     gain = orc.fm_gain(FS / D1, DEV)
@@ -97,9 +100,9 @@ def cascade_oracle_ref_f32(x, chunks, t1, t2, mod):
     return orc.fir("ff", t2, demod, D2), gain
 
 
-def check_against(got, info, log, x, t1, t2, mod, what):
-    ref, gain = cascade_oracle_ref_f32(x, log, t1, t2, mod)
-    n = x.size // 2
+def check_against(got, info, log, x, t1, t2, mod, what, cf32=False):
+    ref, gain = cascade_oracle_ref_f32(x, log, t1, t2, mod, cf32)
+    n = x.size if cf32 else x.size // 2
     assert info["expected"] == orc.chain_num_outputs(n, 101, D1, 1 if mod == "fm" else 0, 129, D2) == ref.size
     assert got.size == info["outputs"] == info["expected"], info
     assert info["monitor_bytes"] == 4 * got.size  # ReadByteCountMonitor saw every byte that reached the host sink
@@ -155,9 +158,14 @@ def test_reference_framework_drives_the_same_graph(tmp_path, binary):
         pytest.skip(f"{exe} not built (oracle/ref/build_ref.sh needs /root/reference at build time)")
     n = (1 << 20) + 4321
     x, t1, t2 = chain_inputs(tmp_path, n, seed=33)
-    got, info, log, dot = run_probe(exe, tmp_path, "stepping", binary, chain_args(tmp_path, "am"))
-    check_against(got, info, log, x, t1, t2, "am", f"{binary} vs cascade oracle")
-    ours, info2, log2, _ = run_probe(build_probe(), tmp_path, "stepping", "ours", chain_args(tmp_path, "am"))
+    # complex-float input: the reference's Int8ToFloat cannot be driven by its own SteppingDriver (Int8ToFloat.cpp:81)
+    z = (x.astype(np.float32) * np.float32(1.0 / 128.0)).view(np.complex64)
+    z.tofile(tmp_path / "in.cf32")
+    args = [str(tmp_path / "in.cf32") if str(a) == str(tmp_path / "in.i8") else a for a in chain_args(tmp_path, "am")] + ["--input", "cf32"]
+    got, info, log, dot = run_probe(exe, tmp_path, "stepping", binary, args)
+    check_against(got, info, log, z, t1, t2, "am", f"{binary} vs cascade oracle", cf32=True)
+    ours, info2, log2, _ = run_probe(build_probe(), tmp_path, "stepping", "ours", args)
+    check_against(ours, info2, log2, z, t1, t2, "am", "this repo's graph (cf32 input) vs cascade oracle", cf32=True)
     assert ours.size == got.size
     assert_close(ours, got, 2e-5, f"this repo's graph vs {binary}")
 
