@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <string>
 #include <vector>
@@ -13,6 +14,7 @@
 #include "digits.h"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
+#include "pfb256_kernels.cuh"
 #include "pfb_kernels.cuh"
 
 using namespace b200sdr;
@@ -67,6 +69,9 @@ struct b200sdr_channelizer {
   int* dPfbBin = nullptr;
   int* dPfbOrder = nullptr;
   float2* dPfbRot1 = nullptr;
+  // N = 256 specialisation (pfb256_kernels.cuh): taps in registers, register-resident FFT, two CTAs per SM
+  unsigned pfb256QN = 0;  // 0: not taken
+  float4* dPfb256Info = nullptr;
   std::vector<int> hostMods;
   std::string variant;
 };
@@ -88,6 +93,7 @@ B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
   cudaFree(c->dPfbBin);
   cudaFree(c->dPfbOrder);
   cudaFree(c->dPfbRot1);
+  cudaFree(c->dPfb256Info);
   delete c;
 }
 
@@ -283,6 +289,29 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
          upload(pfbBin.data(), pfbBin.size() * sizeof(int), reinterpret_cast<void**>(&c->dPfbBin)) &&
          upload(pfbOrder.data(), pfbOrder.size() * sizeof(int), reinterpret_cast<void**>(&c->dPfbOrder)) &&
          upload(pfbRot1.data(), pfbRot1.size() * sizeof(float2), reinterpret_cast<void**>(&c->dPfbRot1));
+    // the N = 256 kernel: demodulation table in the same modulation-sorted order; needs one channel per bin at most
+    const char* e256 = std::getenv("B200SDR_PFB256");
+    unsigned qn = c->pfbQn <= 9u ? 9u : c->pfbQn <= 17u ? 17u : 0u;
+    bool unique = true;
+    {
+      std::vector<char> seen(256, 0);
+      for (unsigned ch = 0; ch < c->C && c->pfbN == 256u; ch++) {
+        unique = unique && !seen[pfbBin[ch] & 255];
+        seen[pfbBin[ch] & 255] = 1;
+      }
+    }
+    if (ok && c->pfbN == 256u && qn != 0u && unique && pfb256Fits(c->D1, qn) && !(e256 && std::atoi(e256) == 0)) {
+      std::vector<float4> info(256, make_float4(0.0f, 1.0f, 0.0f, 0.0f));
+      for (size_t i = 0; i < pfbOrder.size(); i++) {
+        const unsigned ch = static_cast<unsigned>(pfbOrder[i]);
+        const unsigned bits = ch | (static_cast<unsigned>(pfbBin[ch]) & 255u) << 16 | (mods[ch] == 1 ? 1u << 24 : 0u) | 1u << 25;
+        float w;
+        std::memcpy(&w, &bits, sizeof(w));
+        info[i] = make_float4(gains[ch], pfbRot1[ch].x, pfbRot1[ch].y, w);
+      }
+      ok = upload(info.data(), info.size() * sizeof(float4), reinterpret_cast<void**>(&c->dPfb256Info));
+      if (ok) c->pfb256QN = qn;
+    }
   }
   if (!ok) {
     b200sdr_channelizer_destroy(c);
@@ -294,6 +323,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   if (c->pfb)
     snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched audio FIR", c->pfbN, c->C,
              c->pfbQn, kPfbTileK, kPfbWarps, c->pfbSmem);
+  if (c->pfb256QN)
+    snprintf(buf, sizeof(buf), "pfb<N=256,fp64>(kernel=pfb256<QN=%u>: taps in registers, register FFT 8x8x4, TMA input ring, 2 CTAs/SM x %u threads, "
+             "channels=%u,taps/phase=%u,smem=%u) + batched audio FIR", c->pfb256QN, kP2Threads, c->C, c->pfbQn, pfb256SmemLayout().total);
   c->variant = buf;
   c->hostMods = mods;
   *out = c;
@@ -403,7 +435,38 @@ b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInpu
   if (guard.status != cudaSuccess) return cudaFailC(guard.status, "cudaSetDevice");
 
   cudaError_t e = cudaSuccess;
-  if (c->pfb) {
+  if (c->pfb256QN) {
+    Pfb256Params pp {};
+    pp.in = static_cast<const unsigned char*>(input);
+    pp.out = demodScratch;
+    pp.tapsRe = c->dPfbTapsRe;
+    pp.tapsIm = c->dPfbTapsIm;
+    pp.acc0 = c->dPfbAcc0;
+    pp.twiddle = c->dPfbTwiddle;
+    pp.chanInfo = c->dPfb256Info;
+    pp.nInBytes = static_cast<unsigned long long>(numInputs) * 2ull;
+    pp.nOut = nDemod;
+    pp.outStride = demodStride;
+    pp.D1 = c->D1;
+    pp.Qn = c->pfbQn;
+    pp.C = c->C;
+    pp.anyFm = anyFm ? 1 : 0;
+    pp.forceAm = forceAm ? 1 : 0;
+    auto kernel = c->pfb256QN == 9u ? pfb256Kernel<9> : pfb256Kernel<17>;
+    const unsigned smem = pfb256SmemLayout().total;
+    e = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return cudaFailC(e, "cudaFuncSetAttribute");
+    int sms = kSmCount;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const unsigned long long units = (nDemod + 7) / 8;
+    unsigned grid = 2u * static_cast<unsigned>(sms);
+    const char* eg = std::getenv("B200SDR_PFB256_GRID");  // tests: few CTAs, so that each one walks many blocks
+    if (eg && std::atoi(eg) > 0) grid = static_cast<unsigned>(std::atoi(eg));
+    if (units < grid) grid = static_cast<unsigned>(units);
+    kernel<<<grid, kP2Threads, smem, stream>>>(pp);
+    e = launchStatus();
+    if (e != cudaSuccess) return cudaFailC(e, "pfb256Kernel launch");
+  } else if (c->pfb) {
     PfbParams pp {};
     pp.in = static_cast<const unsigned char*>(input);
     pp.out = demodScratch;

@@ -16,7 +16,7 @@
 //     4-point butterflies per lane in registers, two transposes through the warp's own 4 KB buffer with padded, conflict-free
 //     layouts (33-element rows; the filter bank stores phase r at position r/2 + 128*(r&1) so that its own stores and the
 //     FFT's first loads are conflict-free as well).  Shared-memory traffic per FFT: 20 KB instead of 36 KB, no conflicts.
-//   * Demodulated samples leave through a [channel][32] tile flushed as aligned 128-byte rows every eight rounds.
+//   * Demodulated samples leave through a [channel][32] tile flushed as 128-byte rows every eight rounds.
 //
 // Arithmetic is the first kernel's: fp64 filter bank (int8 -> double by one PRMT, see pfbSample) and fp64 FFT, float
 // demodulation.  Every RF output is a function of its own input window only, so results do not depend on how outputs are
@@ -85,6 +85,7 @@ __host__ __device__ inline bool pfb256Fits(unsigned D1, unsigned QN) {
 
 #ifdef __CUDACC__
 
+__device__ __forceinline__ void p2FenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmulI(double2 a) { return make_double2(-a.y, a.x); }  // a * i
@@ -181,13 +182,13 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
   const unsigned D = prm.D1, C = prm.C;
   const bool fm = prm.anyFm != 0 && prm.forceAm == 0;
 
-  // ---- this CTA's run of demodulated samples: whole blocks of 32 ------------------------------------------------------
-  const unsigned long long blocks = (prm.nOut + 31ull) / 32ull;
-  const unsigned long long perCta = blocks / gridDim.x, extraCta = blocks % gridDim.x;
-  const unsigned long long blk0 = blockIdx.x * perCta + (blockIdx.x < extraCta ? blockIdx.x : extraCta);
-  const unsigned long long blk1 = blk0 + perCta + (blockIdx.x < extraCta ? 1ull : 0ull);
-  if (blk1 == blk0) return;
-  const unsigned long long dBeg = blk0 * 32ull, dEnd = blk1 * 32ull < prm.nOut ? blk1 * 32ull : prm.nOut;
+  // ---- this CTA's run of demodulated samples: a multiple of 8 (32-byte sectors of the output rows, 128-byte input alignment) ---
+  const unsigned long long units = (prm.nOut + 7ull) / 8ull;
+  const unsigned long long perCta = units / gridDim.x, extraCta = units % gridDim.x;
+  const unsigned long long unit0 = blockIdx.x * perCta + (blockIdx.x < extraCta ? blockIdx.x : extraCta);
+  const unsigned long long unit1 = unit0 + perCta + (blockIdx.x < extraCta ? 1ull : 0ull);
+  if (unit1 == unit0) return;
+  const unsigned long long dBeg = unit0 * 8ull, dEnd = unit1 * 8ull < prm.nOut ? unit1 * 8ull : prm.nOut;
   const unsigned nK = static_cast<unsigned>(dEnd - dBeg) + (fm ? 1u : 0u);  // RF outputs dBeg .. dBeg + nK - 1
   const unsigned rounds = (nK + 3u) / 4u;
   const unsigned long long s0Bytes = dBeg * D * 2ull;                        // stream position of round 0
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
       mbarArrive(bar);
       return;
     }
-    fenceProxyAsync();  // generic-proxy reads of the ring bytes being replaced come before the async-proxy write
+    p2FenceProxyAsync();  // generic-proxy reads of the ring bytes being replaced come before the async-proxy write
     mbarExpectTx(bar, bulk);
     const unsigned first = bulk < kP2Ring - ringPos ? bulk : kP2Ring - ringPos;  // a chunk may wrap around the ring's end
     tmaBulkLoad(ring + ringPos, prm.in + start, first, bar);

@@ -147,7 +147,7 @@ __device__ __forceinline__ double pfbSample(unsigned w) {
 }
 
 __global__ void __launch_bounds__(kPfbWarps * 32, 1) pfbKernel(const PfbParams prm) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   const unsigned N = prm.N, Qn = prm.Qn, D = prm.D1, C = prm.C;
   const bool fm = prm.anyFm != 0 && prm.forceAm == 0;
   const PfbSmem lay = pfbSmemLayout(N, Qn, D, C);

@@ -127,14 +127,61 @@ def test_raster_channels_take_the_filter_bank(sdr, monkeypatch, pfb, log2n, bins
     assert ch.variant.startswith(f"pfb<N={n_fft},fp64>" if pfb == "1" else "channel<imma"), ch.variant
 
 
-def test_filter_bank_c5_shape_and_empty_channels(sdr):
+@pytest.mark.parametrize("env", [{}, {"B200SDR_PFB256_GRID": "3"}, {"B200SDR_PFB256_GRID": "1"}, {"B200SDR_PFB256": "0"}])
+def test_filter_bank_c5_shape_and_empty_channels(sdr, monkeypatch, env):
     """C5 shape on the 1/256 raster; most of the 24 channels carry no signal at all, so their level is set by what leaks
-    from the strong ones: the bound is relative to each channel's own level."""
+    from the strong ones: the bound is relative to each channel's own level.  Default kernel = pfb256 (taps in registers,
+    register FFT, TMA input ring); with the grid limited to a few CTAs each one walks hundreds of rounds, so the input
+    ring wraps many times and the lagging FM flush runs on every block; B200SDR_PFB256=0 is the first filter-bank kernel."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     fs = 153.6e6
     freqs = [(c - 12) * 600e3 + 100e3 for c in range(24)]
     mods = [c & 1 for c in range(24)]
     ch, _ = check(sdr, fs, freqs, mods, T1=4097, D1=640, T2=273, D2=5, n=(1 << 21) + 12345, dev_hz=75e3)
     assert ch.variant.startswith("pfb<N=256,fp64>"), ch.variant
+    assert ("kernel=pfb256" in ch.variant) == (env.get("B200SDR_PFB256") != "0"), ch.variant
+
+
+@pytest.mark.parametrize("mods", [[0] * 7, [1] * 7, [0, 1, 1, 0, 1, 0, 0]])
+def test_pfb256_am_only_fm_only_and_counts(sdr, mods):
+    """The N = 256 kernel without FM channels (no lag, flush at the end of a block), with FM channels only, and mixed sets over
+    one audio-decimation period of input lengths (for one residue the AM channels own one more output: the AM tail pass)."""
+    fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5
+    freqs = [(c - 3) * 600e3 * 7 + 100e3 for c in range(7)]
+    differ = 0
+    for extra_rf in range(D2 if 0 in mods and 1 in mods else 1):
+        n = T1 - 1 + D1 * (1500 + extra_rf) + 33
+        ch, _ = check(sdr, fs, freqs, mods, T1, D1, T2, D2, n=n, dev_hz=75e3, seed=50 + extra_rf)
+        assert "kernel=pfb256" in ch.variant, ch.variant
+        counts = [ch.channel_counts(c, n)[1] for c in range(7)]
+        differ += max(counts) - min(counts)
+    assert differ == (1 if 0 in mods and 1 in mods else 0)
+
+
+def test_pfb256_time_segments_concatenate_bit_exactly(sdr, monkeypatch):
+    """Every RF output is a function of its own input window only: overlapped time segments (the multi-GPU decomposition
+    of the filter-bank route) equal the one-shot result bit for bit, whatever the CTA partition of each launch."""
+    fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5
+    freqs = [(c - 6) * 600e3 * 3 + 100e3 for c in range(12)]
+    mods = [c & 1 for c in range(12)]
+    ch, t1, t2, gains = make(sdr, fs, freqs, mods, T1, D1, T2, D2, 75e3)
+    assert "kernel=pfb256" in ch.variant, ch.variant
+    n = (1 << 22) + 4097
+    x = torch.from_numpy(sdr.synth.int8_iq(n, seed=22, sample_rate=fs)).to(DEV)
+    whole = ch.run(x)
+    n_audio = whole.shape[1]
+    for parts in (2, 3, 8):
+        cols = []
+        for i in range(parts):
+            a0, cnt, i0, icnt = ch.segment(n_audio, parts, i)
+            cols.append(ch.run(x[2 * i0: 2 * (i0 + icnt)], cnt))
+        cat = torch.cat(cols, dim=1)
+        assert cat.shape == whole.shape
+        assert torch.equal(cat.view(torch.int32), whole.view(torch.int32)), parts
+    monkeypatch.setenv("B200SDR_PFB256_GRID", "2")  # another CTA partition of the same launch
+    again = ch.run(x)
+    assert torch.equal(again.view(torch.int32), whole.view(torch.int32))
 
 
 def test_filter_bank_equals_direct_route_on_a_shard(sdr, monkeypatch):
@@ -179,12 +226,13 @@ def test_filter_bank_time_segments_concatenate_bit_exactly(sdr):
 _C5_CACHE = {}
 
 
-@pytest.mark.parametrize("pfb", ["1", "0"])
+@pytest.mark.parametrize("pfb", ["256", "1", "0"])
 def test_c5_256_channels_against_the_oracle(sdr, monkeypatch, pfb):
     """BASELINE configs[4] as the bench runs it: 256 channels on the 600 kHz raster alternating AM/FM, 4097 taps / 640, 273
-    audio taps / 5, on 2^24 samples -- EVERY channel of both routes (filter bank with N = 256 fully populated; per-channel
-    int8 GEMM) against the fp64 oracle run channel by channel, with per-channel exact counts."""
-    monkeypatch.setenv("B200SDR_PFB", pfb)
+    audio taps / 5, on 2^24 samples -- EVERY channel of all three routes (the N = 256 filter-bank kernel the bench runs, the
+    first filter-bank kernel, the per-channel int8 GEMM) against the fp64 oracle run channel by channel, with per-channel exact counts."""
+    monkeypatch.setenv("B200SDR_PFB", "0" if pfb == "0" else "1")
+    monkeypatch.setenv("B200SDR_PFB256", "1" if pfb == "256" else "0")
     fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5
     total = 256
     freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]
@@ -193,7 +241,8 @@ def test_c5_256_channels_against_the_oracle(sdr, monkeypatch, pfb):
     t2 = sdr.taps.lowpass(T2, 0.45 * 48e3, fs / D1)
     gain = sdr.fm_gain(fs / D1, 75e3)
     ch = sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=[gain] * total)
-    assert ch.variant.startswith("pfb<N=256,fp64>" if pfb == "1" else "channel<imma"), ch.variant
+    assert ch.variant.startswith("pfb<N=256,fp64>" if pfb != "0" else "channel<imma"), ch.variant
+    assert ("kernel=pfb256" in ch.variant) == (pfb == "256")
     n = (1 << 24) + 640 * 3 + 11
     if "x" not in _C5_CACHE:  # the input and the 256 oracle runs are shared by the two routes
         _C5_CACHE["x"] = sdr.synth.int8_iq(n, seed=0x5D120005 & 0xffff, sample_rate=fs)
