@@ -40,6 +40,7 @@ struct FirParams {
   float inScale;  // 1/128 for int8 input, 1 otherwise
   // direct kernel only: blockIdx.y selects one of several independent streams (batched audio FIR of the channelizer)
   unsigned long long inBatchStride, outBatchStride;  // in input / output elements
+  unsigned winTapChunk;  // window kernel only: taps per phase staged together (multiple of 8; set by the launcher)
 };
 
 #ifdef __CUDACC__

@@ -19,8 +19,12 @@ namespace {
 
 constexpr int kWinThreads = 128;
 constexpr int kWinR = 8;          // consecutive outputs per thread
-constexpr int kWinTapChunk = 32;  // taps (per phase) staged at a time
-constexpr int kWinMaxPhases = 4;  // phases staged at a time (8 measured slower: the 76 KB tile halves the resident CTAs)
+constexpr int kWinMaxTapChunk = 64;  // taps (per phase) staged at a time: ceil(T/D) rounded up to 8, at most this many.  The whole
+                                     // window of a chunk (outputs + taps) is staged per chunk, so a chunk as long as the filter
+                                     // (M <= 64: the audio FIRs, the T/D ~ 16 cells of the sweep) stages every sample ONCE and
+                                     // multiplies no padding zeros; long filters stage half as often as with 32-tap chunks
+// phases staged together: the largest of 5, 4, 2, 1 that divides D (5: the audio decimations 5 and 10 -- one coalesced pass
+// instead of five strided ones; 8 measured slower: the 76 KB tile halves the resident CTAs)
 
 template <typename T>
 struct WinTraits;
@@ -37,15 +41,17 @@ struct WinTraits<float> {
 
 __host__ __device__ constexpr unsigned winPadded(unsigned q) { return q + q / kWinR; }  // one pad element per R
 
-// PC = phases staged together (divides D).  Shared memory: taps [PC][kWinTapChunk] floats, then x [PC][winPadded(rows)] elements.
+// PC = phases staged together (divides D); TC = taps per phase staged together (a multiple of R, prm.winTapChunk).
+// Shared memory: taps [PC][TC] floats, then x [PC][winPadded(BO + TC) + 1] elements.
 template <typename Elem, int PC>
 __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm) {
   extern __shared__ __align__(16) unsigned char wsmem[];
   constexpr unsigned BO = kWinThreads * kWinR;      // outputs per CTA
-  constexpr unsigned ROWS = BO + kWinTapChunk;      // decimated samples staged per phase (window of the tap chunk)
-  constexpr unsigned ROWS_P = winPadded(ROWS) + 1;
+  const unsigned TC = prm.winTapChunk;
+  const unsigned ROWS = BO + TC;                    // decimated samples staged per phase (window of the tap chunk)
+  const unsigned ROWS_P = (winPadded(ROWS) + 1) | 1u;  // odd: the PC rows of one staged sample fall into different banks
   float* sTaps = reinterpret_cast<float*>(wsmem);
-  Elem* sX = reinterpret_cast<Elem*>(wsmem + PC * kWinTapChunk * sizeof(float));
+  Elem* sX = reinterpret_cast<Elem*>(wsmem + PC * kWinMaxTapChunk * sizeof(float));
 
   const unsigned tid = threadIdx.x;
   const unsigned D = prm.D, T = prm.T, M = prm.M;
@@ -57,11 +63,11 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
   for (int r = 0; r < kWinR; r++) acc[r] = WinTraits<Elem>::zero();
 
   for (unsigned p0 = 0; p0 < D; p0 += PC) {
-    for (unsigned m0 = 0; m0 < M; m0 += kWinTapChunk) {
+    for (unsigned m0 = 0; m0 < M; m0 += TC) {
       __syncthreads();  // the previous chunk has been consumed
       // taps of this chunk: sTaps[pc][mm] = h[(m0+mm)*D + p0+pc]
-      for (unsigned i = tid; i < PC * kWinTapChunk; i += kWinThreads) {
-        const unsigned pc = i / kWinTapChunk, mm = i % kWinTapChunk;
+      for (unsigned i = tid; i < PC * TC; i += kWinThreads) {
+        const unsigned pc = i / TC, mm = i % TC;
         const unsigned long long j = static_cast<unsigned long long>(m0 + mm) * D + p0 + pc;
         sTaps[i] = (m0 + mm < M && j < T) ? prm.taps[j] : 0.0f;
       }
@@ -75,14 +81,15 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
 
 #pragma unroll
       for (int pc = 0; pc < PC; pc++) {
-        const Elem* xs = sX + pc * ROWS_P;
-        const float* hs = sTaps + pc * kWinTapChunk;
-        const unsigned base = tid * kWinR;  // this thread's first output within the CTA = first sample of its window
+        const float* hs = sTaps + pc * TC;
+        // this thread's window starts at sample base = 8 tid of the staged row; with one pad element per 8 samples, sample
+        // base + 8 a + b (b < 8) sits at 9 tid + 9 a + b: every offset below is a compile-time constant off `xw`
+        const Elem* xw = sX + pc * ROWS_P + tid * (kWinR + 1);
         Elem w[kWinR];
 #pragma unroll
-        for (int r = 0; r < kWinR - 1; r++) w[r] = xs[winPadded(base + r)];
-#pragma unroll
-        for (int mm = 0; mm < kWinTapChunk; mm += kWinR) {
+        for (int r = 0; r < kWinR - 1; r++) w[r] = xw[r];
+#pragma unroll 2
+        for (unsigned mm = 0; mm < TC; mm += kWinR, xw += kWinR + 1) {
           float h[kWinR];
 #pragma unroll
           for (int u = 0; u < kWinR; u += 4) {
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
 #pragma unroll
           for (int u = 0; u < kWinR; u++) {
             // window slot (u + R - 1) % R receives sample base + mm + u + R - 1; output r uses sample base + r + mm + u
-            w[(u + kWinR - 1) % kWinR] = xs[winPadded(base + mm + u + kWinR - 1)];
+            w[(u + kWinR - 1) % kWinR] = xw[(u + kWinR - 1) + (u + kWinR - 1) / kWinR];
 #pragma unroll
             for (int r = 0; r < kWinR; r++) acc[r] = WinTraits<Elem>::fma(h[u], w[(u + r) % kWinR], acc[r]);
           }
@@ -114,12 +121,16 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
 
 template <typename Elem>
 cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
-  const unsigned pc = prm.D % 4 == 0 ? 4u : prm.D % 2 == 0 ? 2u : 1u;
-  constexpr unsigned BO = kWinThreads * kWinR, ROWS = BO + kWinTapChunk;
-  const size_t smem = pc * kWinTapChunk * sizeof(float) + static_cast<size_t>(pc) * (winPadded(ROWS) + 1) * sizeof(Elem);
+  const unsigned pc = prm.D % 5 == 0 ? 5u : prm.D % 4 == 0 ? 4u : prm.D % 2 == 0 ? 2u : 1u;
+  constexpr unsigned BO = kWinThreads * kWinR;
+  unsigned tc = (prm.M + kWinR - 1) / kWinR * kWinR;
+  if (tc > static_cast<unsigned>(kWinMaxTapChunk)) tc = kWinMaxTapChunk;
+  prm.winTapChunk = tc;
+  const unsigned ROWS = BO + tc;
+  const size_t smem = pc * kWinMaxTapChunk * sizeof(float) + static_cast<size_t>(pc) * ((winPadded(ROWS) + 1) | 1u) * sizeof(Elem);
   const unsigned long long blocks = (prm.nOut + BO - 1) / BO;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  void (*k)(const FirParams) = pc == 4 ? windowKernel<Elem, 4> : pc == 2 ? windowKernel<Elem, 2> : windowKernel<Elem, 1>;
+  void (*k)(const FirParams) = pc == 5 ? windowKernel<Elem, 5> : pc == 4 ? windowKernel<Elem, 4> : pc == 2 ? windowKernel<Elem, 2> : windowKernel<Elem, 1>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;

@@ -90,6 +90,27 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmulI(double2 a) { return make_double2(-a.y, a.x); }  // a * i
 
+// atan2 for the FM discriminator: z = min/max in [0, 1], odd minimax polynomial of degree 15 (max error 1.4e-7 rad in float,
+// fitted on [0, 1]; coefficients derived in tools/atan_fit.py), quadrant by symmetry.  About half the instructions of atan2f.
+__device__ __forceinline__ float p2Atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float z = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+  const float t = z * z;
+  float p = -0.004054363816976547f;
+  p = fmaf(p, t, 0.021862192079424858f);
+  p = fmaf(p, t, -0.055911172181367874f);
+  p = fmaf(p, t, 0.09642109274864197f);
+  p = fmaf(p, t, -0.13908593356609344f);
+  p = fmaf(p, t, 0.1994655877351761f);
+  p = fmaf(p, t, -0.33329859375953674f);
+  p = fmaf(p, t, 0.9999993443489075f);
+  float r = p * z;
+  if (ay > ax) r = 1.57079632679489661923f - r;
+  if (x < 0.0f) r = 3.14159265358979323846f - r;
+  return y < 0.0f ? -r : r;
+}
+
 // 4-point inverse DFT: c[k] <- sum_n c[n] i^(n k)
 __device__ __forceinline__ void dft4inv(double2& c0, double2& c1, double2& c2, double2& c3) {
   const double2 s0 = cadd(c0, c2), s1 = csub(c0, c2), s2 = cadd(c1, c3), s3 = cmulI(csub(c1, c3));
@@ -122,16 +143,18 @@ __device__ __forceinline__ void dft8inv(double2 (&v)[8]) {
 
 // One 256-point inverse FFT by one warp, in place in `buf` (kP2FftStride complex doubles; on entry phase r sits at position
 // r/2 + 128*(r&1)).  On return y[m] = Y[lane + 32 m].
-__device__ __forceinline__ void pfb256Fft(double2* buf, const double2* tw, unsigned lane, double2 (&y)[8]) {
+// twA[(b0 - 1) * 32 + lane] = W256^(b0 * perm(lane)) and twB[(c0 - 1) * 4 + s0] = W32^(c0 * s0): the twiddles in the order the
+// lanes read them (consecutive lanes, consecutive 16-byte entries: no bank conflicts; a gather from the plain 256-entry
+// table costs up to 8 wavefronts per load).
+__device__ __forceinline__ void pfb256Fft(double2* buf, const double2* twA, const double2* twB, unsigned lane, double2 (&y)[8]) {
   // step 1: lane <-> r0 = perm(lane) (even phases on lanes 0..15, odd ones on 16..31); 8-point DFT over r1, r = r0 + 32 r1
-  const unsigned r0 = lane < 16u ? 2u * lane : 2u * (lane - 16u) + 1u;
   const unsigned pos0 = (lane & 15u) + (lane >= 16u ? 128u : 0u);
   double2 v[8];
 #pragma unroll
   for (int r1 = 0; r1 < 8; r1++) v[r1] = buf[pos0 + 16u * r1];
   dft8inv(v);  // v[b0] = A[b0][r0]
 #pragma unroll
-  for (int b0 = 1; b0 < 8; b0++) v[b0] = cmuld(v[b0], tw[(b0 * r0) & 255u]);  // * W256^(b0 r0)
+  for (int b0 = 1; b0 < 8; b0++) v[b0] = cmuld(v[b0], twA[(b0 - 1) * 32 + lane]);  // * W256^(b0 r0)
   __syncwarp();  // every lane has read its inputs: the buffer may be overwritten
 #pragma unroll
   for (int b0 = 0; b0 < 8; b0++) buf[b0 * 33u + lane] = v[b0];  // transpose 1: row b0, column = lane (conflict-free)
@@ -145,7 +168,7 @@ __device__ __forceinline__ void pfb256Fft(double2* buf, const double2* tw, unsig
   }
   dft8inv(v);  // v[c0] = B[b0][c0][s0]
 #pragma unroll
-  for (int c0 = 1; c0 < 8; c0++) v[c0] = cmuld(v[c0], tw[(8u * c0 * s0) & 255u]);  // * W32^(c0 s0)
+  for (int c0 = 1; c0 < 8; c0++) v[c0] = cmuld(v[c0], twB[(c0 - 1) * 4 + s0]);  // * W32^(c0 s0)
   __syncwarp();
 #pragma unroll
   for (int c0 = 0; c0 < 8; c0++) buf[s0 * 64u + b0 + 8u * c0] = v[c0];  // transpose 2: [s0][b0 + 8 c0]
@@ -173,7 +196,8 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
   const Pfb256Smem lay = pfb256SmemLayout();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.barOff);
   const float4* chanInfo = reinterpret_cast<const float4*>(smem + lay.infoOff);
-  double2* tw = reinterpret_cast<double2*>(smem + lay.twOff);
+  double2* twA = reinterpret_cast<double2*>(smem + lay.twOff);  // 7 x 32 entries
+  double2* twB = twA + 7 * 32;                                  // 7 x 4 entries
   double2* fftBufs = reinterpret_cast<double2*>(smem + lay.fftOff);
   float2* yBufs = reinterpret_cast<float2*>(smem + lay.yOff);  // [parity][warp][256]
   float* outTile = reinterpret_cast<float*>(smem + lay.outOff);
@@ -198,7 +222,13 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
   // ---- tables ---------------------------------------------------------------------------------------------------------
   for (unsigned i = tid; i < 256u; i += kP2Threads) {
     reinterpret_cast<float4*>(smem + lay.infoOff)[i] = i < C ? prm.chanInfo[i] : make_float4(0.0f, 1.0f, 0.0f, 0.0f);
-    tw[i] = prm.twiddle[i];
+    if (i < 7u * 32u) {
+      const unsigned b0 = i / 32u + 1u, l = i & 31u, r0 = l < 16u ? 2u * l : 2u * (l - 16u) + 1u;
+      twA[i] = prm.twiddle[(b0 * r0) & 255u];
+    } else if (i < 7u * 32u + 28u) {
+      const unsigned e = i - 7u * 32u, c0 = e / 4u + 1u, s0 = e & 3u;
+      twB[e] = prm.twiddle[(8u * c0 * s0) & 255u];
+    }
   }
   if (tid == 0) {
     for (unsigned i = 0; i < kP2Bars; i++) mbarInit(&bars[i], 1);
@@ -238,13 +268,14 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
   if (tid == 0)
     for (unsigned c = 0; c < live + kP2Prefetch; c++) issueChunk(c);
 
-  const bool anyFmWork = fm;
   unsigned flushed = 0;  // blocks of 32 written out so far
   auto flushBlock = [&](unsigned block) {  // all threads; outTile holds columns of block `block`
     const unsigned long long base = dBeg + 32ull * block;
     const unsigned valid = dEnd - base < 32ull ? static_cast<unsigned>(dEnd - base) : 32u;
-    for (unsigned ch = warp; ch < C; ch += kP2Threads / 32u)
-      if (lane < valid) prm.out[static_cast<unsigned long long>(ch) * prm.outStride + base + lane] = outTile[ch * kP2OutStride + lane];
+    for (unsigned slot = warp; slot < C; slot += kP2Threads / 32u) {  // one 128-byte row per warp and pass
+      const unsigned ch = __float_as_uint(chanInfo[slot].w) & 0xffffu;
+      if (lane < valid) prm.out[static_cast<unsigned long long>(ch) * prm.outStride + base + lane] = outTile[slot * kP2OutStride + lane];
+    }
   };
 
   for (unsigned j = 0; j < rounds; j++) {
@@ -290,47 +321,67 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
     float2* yMine = yBufs + ((j & 1u) * 4u + warp) * 256u;
     {
       double2 y[8];
-      pfb256Fft(fftBufs + warp * kP2FftStride, tw, lane, y);
+      pfb256Fft(fftBufs + warp * kP2FftStride, twA, twB, lane, y);
 #pragma unroll
       for (int m = 0; m < 8; m++) yMine[lane + 32u * m] = make_float2(static_cast<float>(y[m].x), static_cast<float>(y[m].y));
     }
     __syncthreads();  // (B) every warp's Y is visible (the FM discriminator pairs neighbouring outputs)
 
-    // ---- demodulate: AM sample kRel from this warp's Y; FM sample kRel - 1 from the predecessor's Y and this one ----
-    const float2* yPrev = warp > 0 ? yMine - 256 : yBufs + (((j & 1u) ^ 1u) * 4u + 3u) * 256u;
-    auto demodulate = [&](bool doAm, bool doFm) {
-      const bool amOk = doAm && kRel < static_cast<unsigned>(dEnd - dBeg);
-      const bool fmOk = doFm && kRel >= 1u && kRel - 1u < static_cast<unsigned>(dEnd - dBeg) && kRel < nK;
-      if (!amOk && !fmOk) return;
-      for (unsigned i = lane; i < C; i += 32u) {
-        const float4 info = chanInfo[i];
+    // ---- demodulate the round's four RF outputs: thread <-> channel slots tid and tid + 128 (slots are sorted by modulation, so
+    // a warp runs ONE kind per pass: in C5 every thread owns one AM and one FM channel).  AM sample k comes from Y[k]; FM sample
+    // k - 1 pairs Y[k - 1] (the previous output; for the round's first one the previous round's last) with Y[k].
+    const float2* yRound = yBufs + (j & 1u) * 4u * 256u;
+    const float2* yLast = yBufs + (((j & 1u) ^ 1u) * 4u + 3u) * 256u;
+    const unsigned nValid = static_cast<unsigned>(dEnd - dBeg);
+    auto demodulate = [&](bool firstFmOnly, bool skipFirstFm) {
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const unsigned slot = tid + 128u * half;
+        if (slot >= C) continue;
+        const float4 info = chanInfo[slot];
         const unsigned bits = __float_as_uint(info.w);
-        const unsigned ch = bits & 0xffffu, bin = (bits >> 16) & 0xffu;
+        const unsigned bin = (bits >> 16) & 0xffu;
         const bool isFm = ((bits >> 24) & 1u) != 0 && fm;
-        const float2 y = yMine[bin];
+        float* row = outTile + slot * kP2OutStride;
         if (!isFm) {
-          if (amOk) outTile[ch * kP2OutStride + (kRel & 31u)] = sqrtf(fmaf(y.x, y.x, y.y * y.y));
-        } else if (fmOk) {
-          const float2 c = yPrev[bin];
-          const float2 d = make_float2(fmaf(y.y, c.y, y.x * c.x), fmaf(y.y, c.x, -y.x * c.y));
-          const float2 e = make_float2(fmaf(d.x, info.y, -d.y * info.z), fmaf(d.x, info.z, d.y * info.y));
-          outTile[ch * kP2OutStride + ((kRel - 1u) & 31u)] = info.x * atan2f(e.y, e.x);
+          if (firstFmOnly) continue;
+#pragma unroll
+          for (int o = 0; o < 4; o++) {
+            const unsigned k = 4u * j + o;
+            const float2 y = yRound[o * 256 + bin];
+            const float p = fmaf(y.x, y.x, y.y * y.y);
+            if (k < nValid) row[k & 31u] = p > 0.0f ? p * rsqrtf(p) : 0.0f;
+          }
+        } else {
+          float2 c = yLast[bin];
+#pragma unroll
+          for (int o = 0; o < 4; o++) {
+            const unsigned k = 4u * j + o;
+            const float2 y = yRound[o * 256 + bin];
+            const bool wanted = o == 0 ? !skipFirstFm : !firstFmOnly;
+            if (wanted && k >= 1u && k - 1u < nValid && k < nK) {
+              const float2 d = make_float2(fmaf(y.y, c.y, y.x * c.x), fmaf(y.y, c.x, -y.x * c.y));
+              const float2 e = make_float2(fmaf(d.x, info.y, -d.y * info.z), fmaf(d.x, info.z, d.y * info.y));
+              row[(k - 1u) & 31u] = info.x * p2Atan2(e.y, e.x);
+            }
+            c = y;
+          }
         }
       }
     };
-    if (anyFmWork) {
-      // FM samples lag one RF output: block b is complete once round 8 (b + 1) has produced FM sample 32 b + 31 (warp 0)
+    if (fm) {
+      // FM samples lag one RF output: block b is complete once round 8 (b + 1) has produced FM sample 32 b + 31
       if (j > 0 && (j & 7u) == 0) {
-        if (warp == 0) demodulate(false, true);
+        demodulate(true, false);
         __syncthreads();
         flushBlock(flushed++);
         __syncthreads();
-        demodulate(true, warp != 0);
+        demodulate(false, true);
       } else {
-        demodulate(true, true);
+        demodulate(false, false);
       }
     } else {
-      demodulate(true, false);
+      demodulate(false, false);
       if ((j & 7u) == 7u) {
         __syncthreads();
         flushBlock(flushed++);  // the next round's demodulation starts behind its own barriers (A), (B)
