@@ -90,7 +90,6 @@ struct b200sdr_chain {
   float* dToepTaps2 = nullptr;  // audio taps zero-padded to a multiple of 4 (one bulk copy in the kernel)
   float toepScale[3] = {0.0f, 0.0f, 0.0f};
   float2 rot1 = make_float2(1.0f, 0.0f);
-  std::vector<float> hostTaps2;  // audio taps (host copy: the tiled audio route passes them as kernel parameters)
   std::string variant;
 
   // host-buffer path
@@ -191,7 +190,6 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_create(const b200sdr_chain_config* c
   c->T1 = static_cast<unsigned>(cfg->rf_tap_count);
   c->D1 = cfg->rf_decimation == 0 ? 1u : static_cast<unsigned>(cfg->rf_decimation);  // Fir.cpp:119
   c->T2 = cfg->audio_taps ? static_cast<unsigned>(cfg->audio_tap_count) : 0u;
-  if (c->T2) c->hostTaps2.assign(cfg->audio_taps, cfg->audio_taps + c->T2);
   c->D2 = cfg->audio_decimation == 0 ? 1u : static_cast<unsigned>(cfg->audio_decimation);
   c->phaseStep = c->mix ? phaseStepOf(cfg->frequency, cfg->sample_rate) : 0;
   c->fmGain = cfg->fm_gain;
@@ -436,7 +434,6 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_run(
     prm.s0 = c->toepScale[0];
     prm.s1 = c->toepScale[1];
     prm.s2 = c->toepScale[2];
-    if (toepTiled(c->T2, c->D2)) std::memcpy(prm.taps2c, c->hostTaps2.data(), sizeof(float) * c->T2);
     CUDA_OR_RETURN(launchToeplitz(c->toepPlan, prm, stream));
     return B200SDR_OK;
   }

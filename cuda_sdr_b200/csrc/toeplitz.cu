@@ -88,8 +88,8 @@ ToepPlan planToeplitz(unsigned T1, unsigned D1, int mod, unsigned T2, unsigned D
         const unsigned OTW = 64u * G - fm, OT = warps * OTW;
         const unsigned span = (T2 - 1u + OT - 1u) / OT;  // tiles an audio window reaches back
         if (span > kToepLines - 2u) continue;
-        if (toepMirror(T2, D2) > OT) continue;  // keep the mirror inside the first tile of the ring (longer audio filters: other routes)
-        const ToepSmem lay = toepSmemLayout(p.Q, T2, D2, OT, warps, stages, slotBytes);
+        if (((T2 + 3u) & ~3u) > OT) continue;  // keep the mirror inside the first tile of the ring (longer audio filters: other routes)
+        const ToepSmem lay = toepSmemLayout(p.Q, T2, OT, warps, stages, slotBytes);
         if (lay.total > kSmemPerSm - kSmemPerCtaReserve) continue;
         unsigned ctas = kSmemPerSm / (lay.total + kSmemPerCtaReserve);
         const unsigned maxByThreads = 2048u / (32u * (warps + audioWarps));
@@ -201,8 +201,6 @@ cudaError_t launchToeplitz(const ToepPlan& plan, ToepParams prm, cudaStream_t st
   prm.slotBytes = plan.slotBytes;
   prm.blockBytes = plan.blockBytes;
   prm.span = plan.span;
-  prm.mirror = toepMirror(prm.T2, prm.D2);
-  prm.tiled = toepTiled(prm.T2, prm.D2) && envInt("B200SDR_TOEP_TILED_AUDIO", 1) != 0 ? 1u : 0u;
   static const int prefetch = envInt("B200SDR_TOEP_PREFETCH", 0);
   prm.prefetch = prefetch < 0 ? 0u : static_cast<unsigned>(prefetch);
   prm.boxBytes = plan.boxBytes;

@@ -37,9 +37,6 @@
 
 namespace b200sdr {
 
-constexpr unsigned kToepAudioR = 5;          // tiled audio route: consecutive outputs per lane (odd, so that the lane stride R * D2 is odd)
-constexpr unsigned kToepMaxConstTaps = 512;  // audio taps that fit next to the other kernel parameters (4 KB parameter space)
-
 struct ToepParams {
   const unsigned char* in;  // interleaved int8 I,Q; 16-byte aligned
   float* out;               // audio outputs
@@ -62,26 +59,16 @@ struct ToepParams {
   float gain;
   float2 rot1;              // exp(j*w*D1) (FM only)
   float s0, s1, s2;         // value = acc0*s0 + acc1*s1 + acc2*s2
-  unsigned mirror;          // demod samples mirrored past the end of the ring (multiple of 4): toepMirror(T2, D2)
-  unsigned tiled;           // 1: odd D2 -- the register-tiled audio FIR (kToepAudioR consecutive outputs per lane, taps below)
-  float taps2c[kToepMaxConstTaps];  // the audio taps again, in the kernel-parameter constant bank (tiled route only): a tap is
-                                    // warp-uniform there, so reading it costs no shared-memory wavefront
 };
 
 constexpr unsigned kToepLines = 4;  // tiles in the demod ring
-
-// demod samples mirrored past the ring's end: a window (T2), plus -- on the tiled route -- the R - 1 further windows of a lane
-__host__ __device__ inline unsigned toepTiled(unsigned T2, unsigned D2) { return (D2 & 1u) != 0 && T2 <= kToepMaxConstTaps ? 1u : 0u; }
-__host__ __device__ inline unsigned toepMirror(unsigned T2, unsigned D2) {
-  return (T2 + (toepTiled(T2, D2) ? (kToepAudioR - 1u) * D2 : 0u) + 3u) & ~3u;
-}
 
 struct ToepSmem {
   unsigned bFragOff, taps2Off, dmOff, slotOff, total;
 };
 
 // barriers: tileDone[4] at 0, tileFull[4] at 32, constants at 64, full[NW*S] at 128 (NW*S <= 48)
-__host__ __device__ inline ToepSmem toepSmemLayout(unsigned Q, unsigned T2, unsigned D2, unsigned OT, unsigned NW, unsigned S, unsigned slotBytes) {
+__host__ __device__ inline ToepSmem toepSmemLayout(unsigned Q, unsigned T2, unsigned OT, unsigned NW, unsigned S, unsigned slotBytes) {
   ToepSmem s;
   unsigned off = 512;
   s.bFragOff = off;
@@ -89,7 +76,7 @@ __host__ __device__ inline ToepSmem toepSmemLayout(unsigned Q, unsigned T2, unsi
   s.taps2Off = off;
   off += ((T2 + 3u) & ~3u) * 4u;
   s.dmOff = off;
-  off += (kToepLines * OT + toepMirror(T2, D2)) * 4u;  // ring + mirror
+  off += (kToepLines * OT + ((T2 + 3u) & ~3u)) * 4u;  // ring + mirror
   off = (off + 1023u) & ~1023u;
   s.slotOff = off;
   off += NW * S * slotBytes;
@@ -137,8 +124,8 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
   const unsigned OT = NW * OTW;       // demod outputs per tile
   const unsigned AS = 8u * D;         // A-row stride (4 outputs)
   const unsigned R = kToepLines * OT; // demod ring, floats
-  const unsigned mirror = prm.mirror, tapsPad = (T2 + 3u) & ~3u;
-  const ToepSmem lay = toepSmemLayout(prm.Q, T2, D2, OT, NW, S, prm.slotBytes);
+  const unsigned mirror = (T2 + 3u) & ~3u;
+  const ToepSmem lay = toepSmemLayout(prm.Q, T2, OT, NW, S, prm.slotBytes);
   uint64_t* tileDone = reinterpret_cast<uint64_t*>(smem);
   uint64_t* constBar = reinterpret_cast<uint64_t*>(smem + 64);
   uint64_t* tileFull = reinterpret_cast<uint64_t*>(smem + 32);
@@ -172,9 +159,9 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
     mbarInit(constBar, 1);
     fenceMbarInit();
     // constants (written when the chain was created): B fragments and audio taps, one bulk copy each
-    mbarExpectTx(constBar, prm.Q * 1536u + tapsPad * 4u);
+    mbarExpectTx(constBar, prm.Q * 1536u + mirror * 4u);
     tmaBulkLoad(smem + lay.bFragOff, prm.bFrag, prm.Q * 1536u, constBar);
-    tmaBulkLoad(smem + lay.taps2Off, prm.taps2, tapsPad * 4u, constBar);
+    tmaBulkLoad(smem + lay.taps2Off, prm.taps2, mirror * 4u, constBar);
   }
   __syncthreads();  // the only CTA-wide barrier
   // Programmatic dependent launch: everything above touches only this CTA's shared memory and constants written when the
@@ -387,47 +374,6 @@ __global__ void __launch_bounds__(384, 1) toepKernel(const ToepParams prm, const
       mbarWait(&tileFull[line], use & 1u);
       unsigned base = line * OT + R - carry;  // ring index of the first unfinished window
       if (base >= R) base -= R;
-      if (prm.tiled) {
-        // Register-tiled route (odd D2): a lane owns kToepAudioR CONSECUTIVE outputs, whose windows overlap in all but D2
-        // samples -- every demod sample is read from shared memory once per lane and feeds up to R multiply-adds (the
-        // thread-per-output form reads it once per output: 273 wavefront-loads per output for C3, against 59 here).  The
-        // lane stride R * D2 is odd, so the 32 loads of a warp hit 32 different banks; the taps come from the constant bank.
-        // Every output accumulates h[0] x[.] ... h[T2-1] x[.] in this order in ONE accumulator, whatever lane it lands on.
-        for (unsigned o0 = 0; o0 < nA; o0 += 32u * kToepAudioR) {
-          const unsigned o = o0 + kToepAudioR * lane;  // this lane's first output
-          unsigned s0 = base + o * D2;
-          while (s0 >= R) s0 -= R;
-          const float* x = ring + s0;
-          float acc[kToepAudioR];
-#pragma unroll
-          for (unsigned r = 0; r < kToepAudioR; r++) acc[r] = 0.0f;
-          if (o < nA) {
-            const unsigned ramp = (kToepAudioR - 1u) * D2;
-            unsigned t = 0;
-            for (; t < ramp; t++) {  // ramp-up: output r starts at t = r D2
-              const float v = x[t];
-#pragma unroll
-              for (unsigned r = 0; r < kToepAudioR; r++)
-                if (t >= r * D2) acc[r] = fmaf(prm.taps2c[t - r * D2], v, acc[r]);
-            }
-#pragma unroll 2
-            for (; t < T2; t++) {    // all R outputs take the sample
-              const float v = x[t];
-#pragma unroll
-              for (unsigned r = 0; r < kToepAudioR; r++) acc[r] = fmaf(prm.taps2c[t - r * D2], v, acc[r]);
-            }
-            for (; t < T2 + ramp; t++) {  // ramp-down: output r ends at t = T2 + r D2
-              const float v = x[t];
-#pragma unroll
-              for (unsigned r = 0; r < kToepAudioR; r++)
-                if (t >= r * D2 && t - r * D2 < T2) acc[r] = fmaf(prm.taps2c[t - r * D2], v, acc[r]);
-            }
-#pragma unroll
-            for (unsigned r = 0; r < kToepAudioR; r++)
-              if (o + r < nA) prm.out[a0 + done + o + r] = acc[r];
-          }
-        }
-      } else
       // each lane works on outputs o and o + 32 at once: two independent dot products
       for (unsigned o = lane; o < nA; o += 64u) {
         const bool two = o + 32u < nA;
