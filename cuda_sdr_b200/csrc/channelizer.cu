@@ -11,11 +11,13 @@
 #include <vector>
 
 #include "channel_kernels.cuh"
+#include "channel_tc_kernels.cuh"
 #include "digits.h"
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
 #include "pfb256_kernels.cuh"
 #include "pfb_kernels.cuh"
+#include "toeplitz_dispatch.h"
 
 using namespace b200sdr;
 
@@ -59,6 +61,11 @@ struct b200sdr_channelizer {
   float* dGain = nullptr;
   int* dMod = nullptr;
   float* dTaps2 = nullptr;
+  // tcgen05 route of the per-channel GEMM (channel_tc_kernels.cuh): B as [group][240 columns][K] int8, K-major
+  bool tc = false;
+  unsigned tcGroups = 0, tcSlabs = 0;
+  signed char* dBtc = nullptr;
+  CUtensorMap tcMapB {};
   // polyphase-filter-bank route (pfb_kernels.cuh): every channel on a raster fs/N with one common offset
   bool pfb = false;
   unsigned pfbN = 0, pfbQn = 0, pfbSmem = 0;
@@ -80,6 +87,7 @@ B200SDR_EXPORT void b200sdr_channelizer_destroy(b200sdr_channelizer* c) {
   if (!c) return;
   DeviceGuard guard(c->device);
   cudaFree(c->dTail);
+  cudaFree(c->dBtc);
   cudaFree(c->dBFrag);
   cudaFree(c->dRot);
   cudaFree(c->dScale);
@@ -147,6 +155,15 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   std::vector<int> mods(c->C, 0);
   std::vector<double> B(static_cast<size_t>(K) * NCOL);
   const double twoPi = 6.283185307179586476925286766559;
+  // tcgen05 route: needs whole 128-byte K-slabs (K = 2 D1 a multiple of 128) and the tensor-map encoder of the driver
+  const unsigned Ktc = 2u * c->D1;
+  {
+    const char* e = std::getenv("B200SDR_CHANNEL_TC");
+    c->tc = !(e && std::atoi(e) == 0) && Ktc % 128u == 0;
+  }
+  c->tcGroups = (c->C + kTcChannels - 1) / kTcChannels;
+  c->tcSlabs = Ktc / 128u;
+  std::vector<signed char> Btc(c->tc ? static_cast<size_t>(c->tcGroups) * kTcN * Ktc : 0, 0);
   for (unsigned ch = 0; ch < c->C; ch++) {
     const uint64_t step = phaseStepOf(cfg->frequencies[ch], cfg->sample_rate);
     auto phasor = [&](uint64_t turns, double& re, double& im) {
@@ -196,6 +213,10 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
               int dg[3];
               balancedDigits(B[static_cast<size_t>(k) * NCOL + n], fx.scale, dg);
               for (int d = 0; d < 3; d++) word[d] |= (static_cast<unsigned>(dg[d]) & 0xffu) << (8u * e);
+              if (c->tc && k < Ktc) {  // the same digits, K-major: row = channel-in-group * 48 + digit * 16 + column
+                const size_t rowBase = static_cast<size_t>(ch / kTcChannels) * kTcN + (ch % kTcChannels) * 48u + n;
+                for (int d = 0; d < 3; d++) Btc[(rowBase + 16u * d) * Ktc + k] = static_cast<signed char>(dg[d]);
+              }
             }
             const unsigned n = local * c->NTC + nt;
             for (unsigned d = 0; d < 3; d++)
@@ -246,6 +267,8 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
     }
   }
 
+  if (c->pfb) c->tc = false;  // the filter bank takes the launch: the GEMM tables of the tcgen05 route are not needed
+
   DeviceGuard guard(c->device);
   b200sdr_status st = B200SDR_OK;
   auto upload = [&](const void* host, size_t bytes, void** dev) -> bool {
@@ -265,6 +288,20 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
        upload(gains.data(), gains.size() * sizeof(float), reinterpret_cast<void**>(&c->dGain)) &&
        upload(mods.data(), mods.size() * sizeof(int), reinterpret_cast<void**>(&c->dMod)) &&
        upload(cfg->audio_taps, sizeof(float) * c->T2, reinterpret_cast<void**>(&c->dTaps2));
+  if (ok && c->tc) {
+    const EncodeTiled encode = encodeTiled();
+    if (!encode) {
+      c->tc = false;
+    } else {
+      ok = upload(Btc.data(), Btc.size(), reinterpret_cast<void**>(&c->dBtc));
+      const cuuint64_t dims[2] = {Ktc, static_cast<cuuint64_t>(c->tcGroups) * kTcN};
+      const cuuint64_t strides[1] = {Ktc};
+      const cuuint32_t box[2] = {128u, kTcN}, es[2] = {1u, 1u};
+      if (ok && encode(&c->tcMapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->dBtc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        c->tc = false;
+    }
+  }
   if (ok && c->anyFm && c->anyAm) {
     const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->dTail), sizeof(float) * c->C);
     if (e != cudaSuccess) {
@@ -320,6 +357,9 @@ B200SDR_EXPORT b200sdr_status b200sdr_channelizer_create(const b200sdr_channeliz
   char buf[200];
   snprintf(buf, sizeof(buf), "channel<imma,NTC=%u>(channels=%u,groups=%u x %d,warps=%u,rowsTile=%u,kSteps=%u,M=%u) + batched direct FIR", c->NTC,
            c->C, c->groups, kChanNC, c->warps, c->warps * 32u, c->KS, c->M);
+  if (c->tc)
+    snprintf(buf, sizeof(buf), "channel<tcgen05,kind::i8>(channels=%u,groups=%u x %u,tile=128 rows x 240 columns,kSlabs=%u,M=%u,stages=%u,TMEM=2x256 columns) "
+             "+ batched audio FIR", c->C, c->tcGroups, kTcChannels, c->tcSlabs, c->M, kTcStages);
   if (c->pfb)
     snprintf(buf, sizeof(buf), "pfb<N=%u,fp64>(channels=%u,taps/phase=%u,tile=%u RF outputs,warps=%u,smem=%u) + batched audio FIR", c->pfbN, c->C,
              c->pfbQn, kPfbTileK, kPfbWarps, c->pfbSmem);
@@ -499,16 +539,61 @@ b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInpu
     e = launchStatus();
     if (e != cudaSuccess) return cudaFailC(e, "pfbKernel launch");
   } else {
+  // ---- tcgen05 route: every output whose rows are complete in the input; the few that need the input's last, partial
+  // row (zero-filled by the legacy kernel's loads) stay on the legacy kernel below ----
+  size_t doneTc = 0;
+  if (c->tc) {
+    const size_t rowsAvail = numInputs / c->D1;
+    const size_t fit = rowsAvail + (anyFm ? 0 : 1) > c->M ? rowsAvail + (anyFm ? 0 : 1) - c->M : 0;
+    const size_t nTc = fit < nDemod ? fit : nDemod;
+    const EncodeTiled encode = encodeTiled();
+    if (nTc > 0 && encode) {
+      const unsigned Ktc = 2u * c->D1;
+      CUtensorMap mapA;
+      const cuuint64_t dims[2] = {Ktc, rowsAvail};
+      const cuuint64_t strides[1] = {Ktc};
+      const cuuint32_t box[2] = {128u, kTcRows}, es[2] = {1u, 1u};
+      if (encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(input), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return chainFail(B200SDR_RUNTIME_ERROR, "cuTensorMapEncodeTiled failed for the channelizer input");
+      ChannelTcParams tp {};
+      tp.out = demodScratch;
+      tp.rot = c->dRot;
+      tp.digitScale = c->dScale;
+      tp.gain = c->dGain;
+      tp.mod = c->dMod;
+      tp.nOut = nTc;
+      tp.outStride = demodStride;
+      tp.M = c->M;
+      tp.kSlabs = c->tcSlabs;
+      tp.numChannels = c->C;
+      tp.groups = c->tcGroups;
+      tp.tiles = (nTc + (kTcRows - c->M) - 1) / (kTcRows - c->M);
+      tp.forceAm = forceAm ? 1 : 0;
+      const unsigned smem = channelTcSmemLayout(c->M).total;
+      e = cudaFuncSetAttribute(reinterpret_cast<const void*>(channelTcKernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return cudaFailC(e, "cudaFuncSetAttribute");
+      int sms = kSmCount;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+      const unsigned long long items = tp.tiles * tp.groups;
+      const unsigned grid = items < static_cast<unsigned long long>(sms) ? static_cast<unsigned>(items) : static_cast<unsigned>(sms);
+      channelTcKernel<<<grid, kTcThreads, smem, stream>>>(tp, mapA, c->tcMapB);
+      e = launchStatus();
+      if (e != cudaSuccess) return cudaFailC(e, "channelTcKernel launch");
+      doneTc = nTc;
+    }
+  }
+  if (doneTc < nDemod) {
   ChannelParams prm {};
-  prm.in = static_cast<const unsigned char*>(input);
-  prm.out = demodScratch;
+  prm.in = static_cast<const unsigned char*>(input) + 2 * doneTc * c->D1;
+  prm.out = demodScratch + doneTc;
   prm.bFrag = c->dBFrag;
   prm.rot = c->dRot;
   prm.digitScale = c->dScale;
   prm.gain = c->dGain;
   prm.mod = c->dMod;
-  prm.nIn = numInputs;
-  prm.nOut = nDemod;
+  prm.nIn = numInputs - doneTc * c->D1;
+  prm.nOut = nDemod - doneTc;
   prm.outStride = demodStride;
   prm.D1 = c->D1;
   prm.M = c->M;
@@ -520,7 +605,7 @@ b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInpu
   const size_t ring = static_cast<size_t>(kChanStages) * (static_cast<size_t>(rowsTile) * kChanARow + static_cast<size_t>(NT) * 3u * 64u * 4u);
   const size_t park = static_cast<size_t>(kChanNC) * c->M * rowsTile * sizeof(float2);
   const size_t smem = ring > park ? ring : park;
-  const unsigned long long tiles = (nDemod + OT - 1) / OT;
+  const unsigned long long tiles = (nDemod - doneTc + OT - 1) / OT;
   if (tiles > 65535ull * 32768ull) return chainFail(B200SDR_OUT_OF_RANGE, "block too long");
   auto kernel = c->NTC == 1 ? channelKernel<1> : channelKernel<2>;
   if (smem > 48 * 1024) {
@@ -531,6 +616,7 @@ b200sdr_status runImpl(b200sdr_channelizer* c, const void* input, size_t numInpu
   kernel<<<dim3(c->groups, static_cast<unsigned>(tiles)), c->warps * 32u, smem, stream>>>(prm);
   e = launchStatus();
   if (e != cudaSuccess) return cudaFailC(e, "channelKernel launch");
+  }
   }
 
   FirParams fir {};

@@ -9,6 +9,19 @@
 
 namespace b200sdr {
 
+// cuTensorMapEncodeTiled lives in the driver library; fetch it through the runtime so libb200sdr.so has no link-time
+// dependency on libcuda (the library must load, and export its symbols, on a box without a driver)
+EncodeTiled encodeTiled() {
+  static EncodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiled>(p);
+  }();
+  return fn;
+}
+
 namespace {
 
 int envInt(const char* name, int fallback) {
@@ -20,21 +33,6 @@ constexpr unsigned kSmemPerSm = 227u * 1024u;
 constexpr unsigned kSmemPerCtaReserve = 1024u;
 
 using ToepKernel = void (*)(const ToepParams, const CUtensorMap);
-
-// cuTensorMapEncodeTiled lives in the driver library; fetch it through the runtime so libb200sdr.so has no link-time
-// dependency on libcuda (the library must load, and export its symbols, on a box without a driver)
-using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiled encodeTiled() {
-  static EncodeTiled fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-    (void)cudaGetLastError();
-    return reinterpret_cast<EncodeTiled>(p);
-  }();
-  return fn;
-}
 
 unsigned swizzleSpan(unsigned D1) { return (8u * D1) % 128u == 64u ? 64u : 128u; }
 ToepKernel toepKernelFor(unsigned G, bool magic) {

@@ -2,6 +2,7 @@
 // a Toeplitz view of the raw input.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap and the encoder's signature (types only: no link-time dependency on libcuda)
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -11,6 +12,11 @@
 namespace b200sdr {
 
 struct ToepParams;
+
+// cuTensorMapEncodeTiled, fetched from the driver at run time (nullptr without a driver)
+using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled encodeTiled();
 
 struct ToepPlan {
   bool ok;       // false: shape not supported (D1 not a multiple of 8, no audio FIR, tables too large, or disabled by B200SDR_TOEPLITZ=0)

@@ -42,11 +42,14 @@ def check(sdr, fs, freqs, mods, T1, D1, T2, D2, n, dev_hz=5e3, seed=3):
     return ch, got[:, :n_audio]
 
 
-def test_small_mixed_channels(sdr):
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_small_mixed_channels(sdr, monkeypatch, tc):
+    monkeypatch.setenv("B200SDR_CHANNEL_TC", tc)
     fs = 1.024e6
     freqs = [-300e3, -111e3, 50e3, 222e3, 333e3, -7e3]
     mods = [0, 1, 0, 1, 1, 0]
-    check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=200003)
+    ch, _ = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=200003)
+    assert ch.variant.startswith("channel<tcgen05" if tc == "1" else "channel<imma"), ch.variant
 
 
 def test_few_taps_per_phase_uses_one_n_tile(sdr):
@@ -55,8 +58,11 @@ def test_few_taps_per_phase_uses_one_n_tile(sdr):
     assert "NTC=1" in ch.variant
 
 
-def test_c5_shape_eight_channels(sdr):
-    """C5 per-channel shape (4097 taps, decimate by 640, 273 audio taps, decimate by 5) on an 8-channel slice."""
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_c5_shape_eight_channels(sdr, monkeypatch, tc):
+    """C5 per-channel shape (4097 taps, decimate by 640, 273 audio taps, decimate by 5) on an 8-channel slice, off any raster:
+    the per-channel int8 GEMM, on tcgen05 (UTCIMMA, accumulators in TMEM) and on the legacy IMMA path."""
+    monkeypatch.setenv("B200SDR_CHANNEL_TC", tc)
     fs = 153.6e6
     freqs = [(-4 + i) * 600e3 + 37e3 for i in range(8)]
     mods = [i & 1 for i in range(8)]
@@ -124,7 +130,7 @@ def test_raster_channels_take_the_filter_bank(sdr, monkeypatch, pfb, log2n, bins
     fs, n_fft = 1.024e6, 1 << log2n
     freqs = [7e3 + b * fs / n_fft for b in bins]  # bins above N/2 are negative frequencies (turns are mod 1)
     ch, _ = check(sdr, fs, freqs, mods, T1=400, D1=64, T2=33, D2=5, n=200003)
-    assert ch.variant.startswith(f"pfb<N={n_fft},fp64>" if pfb == "1" else "channel<imma"), ch.variant
+    assert ch.variant.startswith(f"pfb<N={n_fft},fp64>" if pfb == "1" else "channel<"), ch.variant
 
 
 @pytest.mark.parametrize("env", [{}, {"B200SDR_PFB256_GRID": "3"}, {"B200SDR_PFB256_GRID": "1"}, {"B200SDR_PFB256": "0"}])
@@ -226,13 +232,14 @@ def test_filter_bank_time_segments_concatenate_bit_exactly(sdr):
 _C5_CACHE = {}
 
 
-@pytest.mark.parametrize("pfb", ["256", "1", "0"])
+@pytest.mark.parametrize("pfb", ["256", "1", "0", "0-imma"])
 def test_c5_256_channels_against_the_oracle(sdr, monkeypatch, pfb):
     """BASELINE configs[4] as the bench runs it: 256 channels on the 600 kHz raster alternating AM/FM, 4097 taps / 640, 273
-    audio taps / 5, on 2^24 samples -- EVERY channel of all three routes (the N = 256 filter-bank kernel the bench runs, the
-    first filter-bank kernel, the per-channel int8 GEMM) against the fp64 oracle run channel by channel, with per-channel exact counts."""
-    monkeypatch.setenv("B200SDR_PFB", "0" if pfb == "0" else "1")
+    audio taps / 5, on 2^24 samples -- EVERY channel of all four routes (the N = 256 filter-bank kernel the bench runs, the
+    first filter-bank kernel, the per-channel int8 GEMM on tcgen05 / TMEM and on the legacy IMMA path) against the fp64 oracle run channel by channel, with per-channel exact counts."""
+    monkeypatch.setenv("B200SDR_PFB", "0" if pfb.startswith("0") else "1")
     monkeypatch.setenv("B200SDR_PFB256", "1" if pfb == "256" else "0")
+    monkeypatch.setenv("B200SDR_CHANNEL_TC", "0" if pfb == "0-imma" else "1")
     fs, T1, D1, T2, D2 = 153.6e6, 4097, 640, 273, 5
     total = 256
     freqs = [(c - total / 2) * 600e3 + 100e3 for c in range(total)]
@@ -241,7 +248,8 @@ def test_c5_256_channels_against_the_oracle(sdr, monkeypatch, pfb):
     t2 = sdr.taps.lowpass(T2, 0.45 * 48e3, fs / D1)
     gain = sdr.fm_gain(fs / D1, 75e3)
     ch = sdr.Channelizer(fs, freqs, mods, t1, D1, t2, D2, fm_gains=[gain] * total)
-    assert ch.variant.startswith("pfb<N=256,fp64>" if pfb != "0" else "channel<imma"), ch.variant
+    expect = {"256": "pfb<N=256,fp64>", "1": "pfb<N=256,fp64>", "0": "channel<tcgen05", "0-imma": "channel<imma"}[pfb]
+    assert ch.variant.startswith(expect), ch.variant
     assert ("kernel=pfb256" in ch.variant) == (pfb == "256")
     n = (1 << 24) + 640 * 3 + 11
     if "x" not in _C5_CACHE:  # the input and the 256 oracle runs are shared by the two routes
