@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-channelizer", action="store_true", help="leave the C5 sub-record out of an am/wbfm line")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: equal time segments on every GPU instead of segments in proportion to each GPU's measured rate")
     ap.add_argument("--skip-ncu", action="store_true", help="do not measure roofline.traffic with ncu (use the committed capture)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     return ap.parse_args()
@@ -305,9 +307,32 @@ class Ctx:
                 os.close(saved_stdout)
 
     def make_gather(self, floats_per_rank, slabs=3):
-        """b200sdr_gather over all ranks; the 128-byte NCCL id travels from rank 0 through torch.distributed."""
+        """b200sdr_gather over all ranks.  Peer mode first (rank 0's slabs mapped into every rank over NVLink: the kernels store
+        their audio straight into them; the IPC handles travel through torch.distributed), NCCL send/recv if that is unavailable
+        or BENCH_GATHER=nccl (the 128-byte NCCL id then travels from rank 0 the same way)."""
         from cuda_sdr_b200 import sharding
         torch, dist = self.torch, self.dist
+        if self.world > 1 and os.environ.get("BENCH_GATHER", "peer") == "peer":
+            g, ok = None, 1
+            try:
+                g = sharding.Gather(self.rank, self.world, floats_per_rank, slabs=slabs, device=self.local_rank, mode=sharding.Gather.PEER)
+                blob = g.export_blob()
+            except Exception as e:
+                ok, blob = 0, b""
+                print(f"rank {self.rank}: peer-mode gather unavailable ({e})", file=sys.stderr)
+            blobs = self.gather_objects(blob)
+            if ok and all(len(b) == len(blob) and len(b) > 0 for b in blobs):
+                try:
+                    g.import_blobs(b"".join(blobs))
+                except Exception as e:
+                    ok = 0
+                    print(f"rank {self.rank}: peer-mode import failed ({e})", file=sys.stderr)
+            else:
+                ok = 0
+            if min(self.gather_objects(ok)) == 1:
+                return g
+            if g is not None:
+                g.close()
         uid = None
         if self.world > 1:
             t = torch.zeros(128, dtype=torch.uint8, device=self.dev)
@@ -431,22 +456,60 @@ def run_chain(args, ctx):
     chain = sdr.Chain(wl["fs"], wl["f"], wl["t1"], wl["d1"], wl["mod"], fm_gain=wl["gain"], audio_taps=wl["t2"], audio_decim=wl["d2"],
                       device=ctx.local_rank)
     n_rf, n_demod, n_audio = chain.counts(n)
-    x = sdr.synth.device_int8_iq(n, dev, seed=0x5D120001 + rank)  # this rank's time segment of the stream
-    demod = torch.empty(n_demod, dtype=torch.float32, device=dev)
+    balance = world > 1 and not args.no_balance
+    n_alloc = n + (n >> 3) if balance else n  # balanced segments: the faster GPUs take up to 12 % more than the average
+    x_all = sdr.synth.device_int8_iq(n_alloc, dev, seed=0x5D120001 + rank)  # this rank's time segment of the stream
+    x = x_all[: 2 * n]
+    demod = torch.empty(n_demod + (n_demod >> 3), dtype=torch.float32, device=dev)
     first_index = rank * n  # absolute sample index of the segment (mixer phase)
     # Audio of GATHER_EVERY consecutive steps is collected in one of three slabs; a full slab is gathered to rank 0 by ONE grouped
     # NCCL send/recv on the library's side stream while the next slabs fill.  The cadence follows the run length so that at most
     # ~1/4 of the audio can still be in flight when the last kernel ends.
     ge = int(os.environ.get("BENCH_GATHER_EVERY", "0")) or max(1, min(32, args.steps // 4))
     slabs = 3
-    gather = ctx.make_gather([ge * n_audio] * world, slabs) if world > 1 else None
-    if gather is not None:
-        views = [gather.slab(s).view(ge, n_audio) for s in range(slabs)]
-    else:
-        views = [torch.empty(ge, n_audio, dtype=torch.float32, device=dev) for _ in range(slabs)]
     step_no = [0]
     fused = chain.fused
     k_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    # the clock sampler polls every 50 ms and the timed region of a 20-step run lasts ~2 ms: it runs from the warm-up (the same
+    # kernel back to back, the same load) through the timed region, and reports the samples taken under load
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
+    # warm-up, part 1: the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would run
+    # different counts).  Its rate is also what the balanced partition is computed from.
+    scratch_out = torch.empty(n_audio + (n_audio >> 3), dtype=torch.float32, device=dev)
+    extra = 0
+    torch.cuda.synchronize()
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < args.warmup_seconds or extra < 16:
+        chain.process_device(x, first_index, out=scratch_out, scratch=demod)
+        extra += 1
+        if extra % 16 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    my_rate = extra / max(time.perf_counter() - t_warm, 1e-9)
+    # Partition of the stream over the ranks.  The total work of a step is world * 2^log2_block samples whatever the split; with
+    # --no-balance every rank takes exactly its 2^log2_block, otherwise b200sdr_chain_segment_weighted cuts the world-wide run of
+    # audio outputs in proportion to each GPU's measured rate (power-capped GPUs of one box differ by a few per cent, and a step
+    # ends with the slowest), and every rank reads the input segment its outputs need.
+    counts_audio = [n_audio] * world
+    my_in, my_first_in, my_audio = n, first_index, n_audio
+    shares = None
+    if balance:
+        rates = [r if r > 0 else 1.0 for r in ctx.gather_objects(my_rate)]
+        mean = sum(rates) / world
+        weights = [min(max(r / mean, 0.90), 1.10) for r in rates]  # stay inside the allocation whatever a noisy measurement says
+        total_audio = chain.counts(world * n)[2]
+        segs = [chain.segment_weighted(total_audio, weights, r) for r in range(world)]
+        counts_audio = [sg[1] for sg in segs]
+        _, my_audio, my_first_in, my_in = segs[rank]
+        assert my_in <= n_alloc and my_audio <= scratch_out.numel()
+        x = x_all[: 2 * my_in]
+        shares = [sg[3] / n for sg in segs]
+    gather = ctx.make_gather([ge * c for c in counts_audio], slabs) if world > 1 else None
+    if gather is not None:
+        views = [gather.slab(s)[: ge * my_audio].view(ge, my_audio) for s in range(slabs)]
+    else:
+        views = [torch.empty(ge, my_audio, dtype=torch.float32, device=dev) for _ in range(slabs)]
 
     def step(i=None, last=False):
         k = step_no[0]
@@ -456,13 +519,14 @@ def run_chain(args, ctx):
             gather.acquire(slab)  # this slab's previous gather has drained
         if i is not None and not fused:
             k_events[i][0].record()
-        got = chain.process_device(x, first_index, out=views[slab][slot], scratch=demod)  # fused: ONE kernel; else K1 + K2
+        # fused: ONE kernel; else K1 + K2.  Exactly my_audio outputs of the segment that starts at absolute sample my_first_in.
+        got = chain.run(x, my_audio, my_first_in, out=views[slab][slot], scratch=demod, n_in=my_in)
         if i is not None and not fused:
             k_events[i][1].record()
-        assert got.numel() == n_audio
+        assert got.numel() == my_audio
         if slot == ge - 1 or last:
             if gather is not None:
-                gather.submit(slab, [(slot + 1) * n_audio] * world)
+                gather.submit(slab, [(slot + 1) * c for c in counts_audio])
             step_no[0] += ge - 1 - slot  # a partial slab at the end of a phase: start the next phase on a fresh slab
 
     def quiesce():
@@ -470,19 +534,7 @@ def run_chain(args, ctx):
             gather.finish()
         ctx.barrier()
 
-    # warm-up: first the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would run
-    # different counts), then max(W, 3) complete steps including the gather, in lockstep on every rank
-    # the clock sampler polls every 50 ms and the timed region of a 20-step run lasts ~2 ms: it runs from the warm-up (the same
-    # kernel back to back, the same load) through the timed region, and reports the samples taken under load
-    sampler = ClockSampler(ctx.local_rank)
-    sampler.start()
-    extra = 0
-    t_warm = time.perf_counter()
-    while time.perf_counter() - t_warm < args.warmup_seconds:
-        chain.process_device(x, first_index, out=views[0][0], scratch=demod)
-        extra += 1
-        if extra % 16 == 0:
-            torch.cuda.synchronize()
+    # warm-up, part 2: max(W, 3) complete steps including the gather, in lockstep on every rank
     n_warm = max(args.warmup, 3)
     for w in range(n_warm):
         step(last=(w == n_warm - 1))
@@ -509,13 +561,14 @@ def run_chain(args, ctx):
     per_rank = ctx.gather_objects({"rank": rank, "ms_per_step": my_ms / args.steps, "kernel_ms_per_step": my_kernel_ms / args.steps,
                                    "comm_exposed_ms": my_ms - my_kernel_ms, "clocks": clocks})
     gstats = gather.stats() if gather is not None else None
+    gather_mode = gather.mode if gather is not None else 0
 
     # ---- end to end ------------------------------------------------------------------------------------------------
     e2e = None
     if not args.skip_e2e:
         # (1) the C-ABI host call: pinned host buffers, H2D / kernel / D2H double-buffered inside b200sdr_chain_process_host
         xh = torch.empty(2 * n, dtype=torch.int8).pin_memory()
-        xh.copy_(x)
+        xh.copy_(x_all[: 2 * n])
         outh = torch.empty(n_audio, dtype=torch.float32).pin_memory()
         e2e_steps = max(2, min(args.steps, 5))
         chain.process_host(xh, first_index, out=outh)  # warm-up: allocates the staging slots
@@ -543,11 +596,11 @@ def run_chain(args, ctx):
     if rank == 0:
         peak, peak_src = hbm_peak()
         if fused:  # one kernel: 2 B/sample of int8 IQ in, 4 B per audio sample out, nothing in between
-            alg_bytes = 2.0 * n + 4.0 * n_audio
+            alg_bytes = 2.0 * my_in + 4.0 * my_audio  # this rank's segment (rank 0's share when the partition is balanced)
             kernel_name = ("toepKernel" if chain.variant.startswith("toeplitz<") else "chainKernel") + \
                 " (convert+mix+FIR+decimate+demod+audio FIR, persistent, one launch per step)"
         else:      # K1 + K2: the demodulated stream makes one round trip through HBM
-            alg_bytes = 2.0 * n + 8.0 * n_demod + 4.0 * n_audio
+            alg_bytes = 2.0 * my_in + 8.0 * ((my_audio - 1) * wl["d2"] + len(wl["t2"])) + 4.0 * my_audio
             kernel_name = "rowsKernel + directKernel (two launches per step)"
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
@@ -569,8 +622,9 @@ def run_chain(args, ctx):
             "config": config_dict(wl, args.log2_block, extra={
                 "kernel_variant": chain.variant,
                 "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
-                "parallelism": "overlapped time segments, one per GPU, no collective on the filter path; b200sdr_gather (libb200sdr.so): one "
-                               f"grouped NCCL send/recv per {ge} steps of audio to rank 0 on a side stream, 3 slabs" if world > 1 else
+                "parallelism": ("overlapped time segments, one per GPU" + (", lengths balanced by measured GPU rate" if balance else "") +
+                                ", no collective on the filter path; b200sdr_gather (libb200sdr.so): one "
+                                f"grouped NCCL send/recv per {ge} steps of audio to rank 0 on a side stream, 3 slabs") if world > 1 else
                                "single GPU"}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": k_ms,
@@ -579,11 +633,17 @@ def run_chain(args, ctx):
             "per_rank": per_rank, "comm_exposed_ms": max(p["comm_exposed_ms"] for p in per_rank),
         }
         if gstats:
-            line["gather"] = {"steps_per_gather": ge, "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
-                              "bytes_into_rank0_per_step": 4 * n_audio * (world - 1)}
+            line["gather"] = {"transport": "peer memory (kernels store into rank 0's slabs over NVLink; stream-ordered flags)" if gather_mode == 1
+                              else "NCCL grouped send/recv on a side stream",
+                              "steps_per_gather": ge, "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
+                              "bytes_into_rank0_per_step": 4 * sum(counts_audio[1:])}
+        if shares is not None:
+            line["balance"] = {"what": "time segments in proportion to each GPU's rate measured in the warm-up (b200sdr_chain_segment_weighted); "
+                                       "the step's total stays n_gpus * samples_per_gpu_per_step",
+                               "segment_samples_over_average": shares, "warmup_steps_per_second": rates}
         if e2e:
             line["e2e"] = e2e
-    del x, demod, views
+    del x, x_all, demod, views, scratch_out
     if gather is not None:
         gather.close()
     torch.cuda.empty_cache()
@@ -750,7 +810,8 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
         if per_rank is not None and world > 1:
             rec["per_rank"] = per_rank
             rec["comm_exposed_ms"] = max(p["comm_exposed_ms"] for p in per_rank)
-            rec["gather"] = {"bytes_into_rank0_per_step": 4 * sum(floats[1:]), "slabs": slabs, "calls": gather.stats()["gathers"]}
+            rec["gather"] = {"bytes_into_rank0_per_step": 4 * sum(floats[1:]), "slabs": slabs, "calls": gather.stats()["gathers"],
+                             "transport": "peer memory" if gather.mode == 1 else "NCCL send/recv"}
     del x, x_mine, scratch, outs
     if gather is not None:
         gather.close()

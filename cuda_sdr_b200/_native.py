@@ -71,7 +71,7 @@ class GatherConfig(C.Structure):
 
     _fields_ = [
         ("struct_size", u32), ("rank", i32), ("world", i32), ("slabs", u32), ("cuda_device", i32),
-        ("floats_per_rank", C.POINTER(sz)), ("nccl_unique_id", vp),
+        ("floats_per_rank", C.POINTER(sz)), ("nccl_unique_id", vp), ("mode", u32), ("reserved", u32),
     ]
 
 
@@ -86,6 +86,7 @@ B200SDR_SYMBOLS = {
     "b200sdr_chain_input_window": (sz, [vp]),
     "b200sdr_phase_step": (u64, [f64, f64]),
     "b200sdr_chain_segment": (u32, [vp, sz, sz, sz, psz, psz, psz, psz]),
+    "b200sdr_chain_segment_weighted": (u32, [vp, sz, sz, C.POINTER(f64), sz, psz, psz, psz, psz]),
     "b200sdr_chain_rf_stage": (u32, [vp, vp, sz, u64, vp, sz, stream_t]),
     "b200sdr_chain_audio_stage": (u32, [vp, vp, vp, sz, stream_t]),
     "b200sdr_chain_run": (u32, [vp, vp, sz, u64, vp, vp, sz, stream_t]),
@@ -104,6 +105,9 @@ B200SDR_SYMBOLS = {
     "b200sdr_nccl_unique_id": (u32, [vp]),
     "b200sdr_gather_create": (u32, [C.POINTER(GatherConfig), C.POINTER(vp)]),
     "b200sdr_gather_destroy": (None, [vp]),
+    "b200sdr_gather_exchange_size": (sz, [vp]),
+    "b200sdr_gather_export": (u32, [vp, vp]),
+    "b200sdr_gather_import": (u32, [vp, vp]),
     "b200sdr_gather_slab": (vp, [vp, u32]),
     "b200sdr_gather_acquire": (u32, [vp, u32, stream_t]),
     "b200sdr_gather_submit": (u32, [vp, u32, psz, stream_t]),

@@ -89,6 +89,14 @@ class Chain:
                        "b200sdr_chain_segment")
         return tuple(x.value for x in v)
 
+    def segment_weighted(self, num_audio: int, weights, index: int):
+        """As segment(), with the outputs split in proportion to `weights` (one positive number per part)."""
+        w = (C.c_double * len(weights))(*[float(x) for x in weights])
+        v = [C.c_size_t() for _ in range(4)]
+        N.check_status(_lib.b200sdr_chain_segment_weighted(self._h, num_audio, len(weights), w, index, *[C.byref(x) for x in v]),
+                       "b200sdr_chain_segment_weighted")
+        return tuple(x.value for x in v)
+
     def set_host_segment(self, input_samples: int):
         N.check_status(_lib.b200sdr_chain_set_host_segment(self._h, input_samples), "set_host_segment")
 

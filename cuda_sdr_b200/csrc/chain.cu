@@ -347,6 +347,29 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_segment(
   return B200SDR_OK;
 }
 
+B200SDR_EXPORT b200sdr_status b200sdr_chain_segment_weighted(
+    const b200sdr_chain* c, size_t numAudio, size_t parts, const double* weights, size_t index, size_t* firstOutput, size_t* outputCount,
+    size_t* firstInput, size_t* inputCount) {
+  if (!weights) return b200sdr_chain_segment(c, numAudio, parts, index, firstOutput, outputCount, firstInput, inputCount);
+  if (!c || parts == 0 || index >= parts) return fail(B200SDR_INVALID_ARGUMENT, "bad segment request");
+  double total = 0.0, before = 0.0, through = 0.0;
+  for (size_t i = 0; i < parts; i++) {
+    if (!(weights[i] > 0.0)) return fail(B200SDR_INVALID_ARGUMENT, "segment weights must be positive");
+    total += weights[i];
+    if (i < index) before += weights[i];
+    if (i <= index) through += weights[i];
+  }
+  // boundaries are rounded from the cumulative weights, so the parts tile [0, numAudio) exactly whatever the weights
+  const size_t first = static_cast<size_t>(std::llround(static_cast<double>(numAudio) * (before / total)));
+  const size_t end = index + 1 == parts ? numAudio : static_cast<size_t>(std::llround(static_cast<double>(numAudio) * (through / total)));
+  const size_t count = end > first ? end - first : 0;
+  if (firstOutput) *firstOutput = first;
+  if (outputCount) *outputCount = count;
+  if (firstInput) *firstInput = first * c->stride();
+  if (inputCount) *inputCount = count == 0 ? 0 : (count - 1) * c->stride() + c->window();
+  return B200SDR_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 B200SDR_EXPORT b200sdr_status b200sdr_chain_rf_stage(
     b200sdr_chain* c, const void* input, size_t numInputs, uint64_t firstSampleIndex, void* output,

@@ -9,8 +9,20 @@
 //
 // NCCL is bound at run time (dlopen "libnccl.so.2"): libb200sdr.so has no link-time dependency on it, single-GPU users
 // never load it, and inside a process that already carries NCCL (PyTorch) the same library instance is used.
+//
+// Two transports:
+//   mode 0 (NCCL)  one grouped ncclSend/ncclRecv per slab on the side stream.
+//   mode 1 (peer)  the gathered slabs of rank 0 are mapped into every rank (CUDA IPC over NVLink / NVSwitch peer memory) and
+//                  b200sdr_gather_slab() hands the kernels THAT memory: the filter kernels store their audio straight into
+//                  rank 0's buffer while they compute, so the exchange costs no kernel, no SM and no extra pass over the data.
+//                  Completion and buffer reuse are sequenced by 32-bit flags written / awaited in stream order
+//                  (cuStreamWriteValue32 / cuStreamWaitValue32): rank r -> rank 0 "slab s holds round n of rank r",
+//                  rank 0 -> rank r "slab s is free again".  Measured on 8 B200: with NCCL's receive kernels on rank 0 the
+//                  persistent filter kernel loses its second CTA per SM while a gather runs (3x per step in a 20-step run);
+//                  with peer stores the step time of rank 0 equals the others'.
 #include <b200sdr/b200sdr.h>
 
+#include <cuda.h>  // CUstream / CUdeviceptr / CUresult (types only; entry points are fetched at run time)
 #include <dlfcn.h>
 
 #include <cstdio>
@@ -78,6 +90,26 @@ const Nccl& nccl() {
   return api;
 }
 
+// stream-ordered 32-bit flag operations of the driver API, fetched at run time like the tensor-map encoder
+using StreamValue32 = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct StreamOps {
+  StreamValue32 write = nullptr, wait = nullptr;
+};
+const StreamOps& streamOps() {
+  static StreamOps ops = [] {
+    StreamOps o;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      o.write = reinterpret_cast<StreamValue32>(p);
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      o.wait = reinterpret_cast<StreamValue32>(p);
+    (void)cudaGetLastError();
+    return o;
+  }();
+  return ops;
+}
+
 b200sdr_status ncclFail(int rc, const char* where) {
   const Nccl& n = nccl();
   return chainFail(B200SDR_RUNTIME_ERROR, std::string(where) + ": " + (n.GetErrorString ? n.GetErrorString(rc) : "NCCL error"));
@@ -112,7 +144,21 @@ struct b200sdr_gather {
   std::vector<cudaEvent_t> filled, drained;
   std::vector<char> everSubmitted;
   uint64_t gathers = 0, floatsMoved = 0;
+  // peer mode
+  int mode = 0;
+  bool imported = false;
+  uint32_t* flags = nullptr;                 // this rank's flag block: [slabs][world] "filled" (used on rank 0) + [slabs] "free"
+  std::vector<float*> remoteSlab;            // rank != 0: rank 0's gathered slabs mapped here
+  std::vector<uint32_t*> remoteFlags;        // rank 0: every rank's flag block; rank != 0: [0] = rank 0's
+  std::vector<uint32_t> round;               // [slabs] submissions so far
+  uint32_t* filledFlag(unsigned slab, int r) const { return flags + slab * world + r; }
+  uint32_t* freeFlagOf(uint32_t* block, unsigned slab) const { return block + slabs * world + slab; }
 };
+
+namespace {
+constexpr size_t kIpcHandleBytes = 64;  // sizeof(cudaIpcMemHandle_t)
+size_t exchangeBytes(const b200sdr_gather* g) { return (static_cast<size_t>(g->slabs) + 1u) * kIpcHandleBytes; }
+}  // namespace
 
 B200SDR_EXPORT b200sdr_status b200sdr_nccl_unique_id(void* id128) {
   if (!id128) return chainFail(B200SDR_INVALID_ARGUMENT, "id128 is null");
@@ -129,6 +175,11 @@ B200SDR_EXPORT void b200sdr_gather_destroy(b200sdr_gather* g) {
   DeviceGuard guard(g->device);
   if (g->side) cudaStreamSynchronize(g->side);
   if (g->comm) nccl().CommDestroy(g->comm);
+  for (float* p : g->remoteSlab)
+    if (p) cudaIpcCloseMemHandle(p);
+  for (size_t r = 0; r < g->remoteFlags.size(); r++)
+    if (g->remoteFlags[r] && g->remoteFlags[r] != g->flags) cudaIpcCloseMemHandle(g->remoteFlags[r]);
+  if (g->flags) cudaFree(g->flags);
   for (float* p : g->local) cudaFree(p);
   for (float* p : g->gathered) cudaFree(p);
   for (cudaEvent_t e : g->filled) cudaEventDestroy(e);
@@ -143,13 +194,18 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config*
   if (cfg->struct_size != sizeof(b200sdr_gather_config)) return chainFail(B200SDR_INVALID_ARGUMENT, "struct_size mismatch");
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world || cfg->slabs < 2 || !cfg->floats_per_rank)
     return chainFail(B200SDR_INVALID_ARGUMENT, "need 0 <= rank < world, slabs >= 2 and floats_per_rank");
-  if (cfg->world > 1 && !cfg->nccl_unique_id) return chainFail(B200SDR_INVALID_ARGUMENT, "nccl_unique_id is required when world > 1");
+  if (cfg->mode > B200SDR_GATHER_PEER) return chainFail(B200SDR_INVALID_ARGUMENT, "unknown gather mode");
+  const bool peer = cfg->mode == B200SDR_GATHER_PEER && cfg->world > 1;
+  if (cfg->world > 1 && !peer && !cfg->nccl_unique_id) return chainFail(B200SDR_INVALID_ARGUMENT, "nccl_unique_id is required when world > 1");
+  if (peer && (!streamOps().write || !streamOps().wait)) return chainFail(B200SDR_RUNTIME_ERROR, "the driver lacks cuStreamWriteValue32 / cuStreamWaitValue32");
   b200sdr_gather* g = new (std::nothrow) b200sdr_gather();
   if (!g) return chainFail(B200SDR_OUT_OF_MEMORY, "host allocation failed");
   g->device = cfg->cuda_device;
   g->rank = cfg->rank;
   g->world = cfg->world;
   g->slabs = cfg->slabs;
+  g->mode = peer ? 1 : 0;
+  g->round.assign(cfg->slabs, 0u);
   g->floatsOf.assign(cfg->floats_per_rank, cfg->floats_per_rank + cfg->world);
   g->offsetOf.resize(cfg->world);
   for (int r = 0; r < cfg->world; r++) {
@@ -181,7 +237,14 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config*
   }
   if (e != cudaSuccess) return fail(cudaFailG(e, "allocating the gather slabs"));
   g->everSubmitted.assign(g->slabs, 0);
-  if (g->world > 1) {
+  if (peer) {
+    const size_t words = static_cast<size_t>(g->slabs) * g->world + g->slabs;
+    e = cudaMalloc(reinterpret_cast<void**>(&g->flags), sizeof(uint32_t) * words);
+    if (e == cudaSuccess) e = cudaMemset(g->flags, 0, sizeof(uint32_t) * words);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(cudaFailG(e, "allocating the gather flags"));
+  }
+  if (g->world > 1 && !peer) {
     const Nccl& n = nccl();
     if (!n.ok) return fail(chainFail(B200SDR_RUNTIME_ERROR, n.why));
     NcclUniqueId id;
@@ -194,12 +257,78 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config*
   return B200SDR_OK;
 }
 
-B200SDR_EXPORT float* b200sdr_gather_slab(b200sdr_gather* g, uint32_t slab) { return g && slab < g->slabs ? g->local[slab] : nullptr; }
+B200SDR_EXPORT float* b200sdr_gather_slab(b200sdr_gather* g, uint32_t slab) {
+  if (!g || slab >= g->slabs) return nullptr;
+  if (g->mode == 0) return g->local[slab];
+  if (!g->imported) return nullptr;  // the peer mappings exist after b200sdr_gather_import
+  return (g->rank == 0 ? g->gathered[slab] : g->remoteSlab[slab]) + g->offsetOf[g->rank];  // rank 0's memory, this rank's part
+}
+
+B200SDR_EXPORT size_t b200sdr_gather_exchange_size(const b200sdr_gather* g) { return g && g->mode == 1 ? exchangeBytes(g) : 0; }
+
+// This rank's blob: the IPC handles of rank 0's gathered slabs (zero elsewhere) and of this rank's flag block.
+B200SDR_EXPORT b200sdr_status b200sdr_gather_export(b200sdr_gather* g, void* blob) {
+  if (!g || !blob || g->mode != 1) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
+  DeviceGuard guard(g->device);
+  unsigned char* out = static_cast<unsigned char*>(blob);
+  std::memset(out, 0, exchangeBytes(g));
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == kIpcHandleBytes, "cudaIpcMemHandle_t is 64 bytes");
+  if (g->rank == 0)
+    for (unsigned s = 0; s < g->slabs; s++) {
+      CUDA_OR_FAIL(cudaIpcGetMemHandle(&h, g->gathered[s]));
+      std::memcpy(out + s * kIpcHandleBytes, &h, sizeof(h));
+    }
+  CUDA_OR_FAIL(cudaIpcGetMemHandle(&h, g->flags));
+  std::memcpy(out + g->slabs * kIpcHandleBytes, &h, sizeof(h));
+  return B200SDR_OK;
+}
+
+// blobs: `world` blobs of b200sdr_gather_exchange_size() bytes each, in rank order (gathered by the caller's transport)
+B200SDR_EXPORT b200sdr_status b200sdr_gather_import(b200sdr_gather* g, const void* blobs) {
+  if (!g || !blobs || g->mode != 1) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
+  if (g->imported) return B200SDR_OK;
+  DeviceGuard guard(g->device);
+  const unsigned char* in = static_cast<const unsigned char*>(blobs);
+  const size_t each = exchangeBytes(g);
+  cudaIpcMemHandle_t h;
+  g->remoteFlags.assign(g->world, nullptr);
+  g->remoteFlags[g->rank] = g->flags;
+  if (g->rank == 0) {
+    for (int r = 1; r < g->world; r++) {  // every rank's flag block: rank 0 writes their "free" flags
+      std::memcpy(&h, in + r * each + g->slabs * kIpcHandleBytes, sizeof(h));
+      void* p = nullptr;
+      CUDA_OR_FAIL(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      g->remoteFlags[r] = static_cast<uint32_t*>(p);
+    }
+  } else {
+    g->remoteSlab.assign(g->slabs, nullptr);
+    for (unsigned s = 0; s < g->slabs; s++) {  // rank 0's gathered slabs: the kernels of this rank store into them
+      std::memcpy(&h, in + s * kIpcHandleBytes, sizeof(h));
+      void* p = nullptr;
+      CUDA_OR_FAIL(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      g->remoteSlab[s] = static_cast<float*>(p);
+    }
+    std::memcpy(&h, in + g->slabs * kIpcHandleBytes, sizeof(h));
+    void* p = nullptr;
+    CUDA_OR_FAIL(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->remoteFlags[0] = static_cast<uint32_t*>(p);
+  }
+  g->imported = true;
+  return B200SDR_OK;
+}
 
 B200SDR_EXPORT b200sdr_status b200sdr_gather_acquire(b200sdr_gather* g, uint32_t slab, cudaStream_t stream) {
   if (!g || slab >= g->slabs) return chainFail(B200SDR_INVALID_ARGUMENT, "bad slab");
   if (!g->everSubmitted[slab]) return B200SDR_OK;
   DeviceGuard guard(g->device);
+  if (g->mode == 1 && g->rank != 0) {
+    // rank 0 has released round `round[slab]` of this slab (a flag in THIS rank's memory, written by rank 0 in stream order)
+    if (streamOps().wait(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(g->freeFlagOf(g->flags, slab)), g->round[slab],
+                         CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+      return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWaitValue32 failed");
+    return B200SDR_OK;
+  }
   CUDA_OR_FAIL(cudaStreamWaitEvent(stream, g->drained[slab], 0));  // the slab's previous gather has read it
   return B200SDR_OK;
 }
@@ -210,6 +339,30 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_submit(b200sdr_gather* g, uint32_t 
   const size_t* counts = floatsPerRank ? floatsPerRank : g->floatsOf.data();
   for (int r = 0; r < g->world; r++)
     if (counts[r] > g->floatsOf[r]) return chainFail(B200SDR_OUT_OF_RANGE, "more floats than the slab holds");
+  if (g->mode == 1) {
+    if (!g->imported) return chainFail(B200SDR_INVALID_STATE, "b200sdr_gather_import has not been called");
+    const uint32_t round = ++g->round[slab];
+    // "slab holds round `round` of this rank": a flag in RANK 0's memory, written behind the kernels that stored the audio there
+    uint32_t* mine = g->rank == 0 ? g->filledFlag(slab, 0) : g->remoteFlags[0] + slab * g->world + g->rank;
+    if (streamOps().write(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(mine), round, 0) != CUDA_SUCCESS)
+      return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWriteValue32 failed");
+    if (g->rank == 0) {
+      // the side stream collects every rank's flag, marks the slab complete and hands it back to the senders
+      for (int r = 0; r < g->world; r++)
+        if (streamOps().wait(reinterpret_cast<CUstream>(g->side), reinterpret_cast<CUdeviceptr>(g->filledFlag(slab, r)), round, CU_STREAM_WAIT_VALUE_GEQ) !=
+            CUDA_SUCCESS)
+          return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWaitValue32 failed");
+      CUDA_OR_FAIL(cudaEventRecord(g->drained[slab], g->side));
+      for (int r = 1; r < g->world; r++)
+        if (streamOps().write(reinterpret_cast<CUstream>(g->side), reinterpret_cast<CUdeviceptr>(g->freeFlagOf(g->remoteFlags[r], slab)), round, 0) !=
+            CUDA_SUCCESS)
+          return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWriteValue32 failed");
+    }
+    g->everSubmitted[slab] = 1;
+    g->gathers++;
+    for (int r = 0; r < g->world; r++) g->floatsMoved += (g->rank == 0 || r == g->rank) ? counts[r] : 0;
+    return B200SDR_OK;
+  }
   CUDA_OR_FAIL(cudaEventRecord(g->filled[slab], stream));
   CUDA_OR_FAIL(cudaStreamWaitEvent(g->side, g->filled[slab], 0));
   if (g->rank == 0 && counts[0])
@@ -235,8 +388,16 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_submit(b200sdr_gather* g, uint32_t 
 B200SDR_EXPORT b200sdr_status b200sdr_gather_finish(b200sdr_gather* g, cudaStream_t stream) {
   if (!g) return chainFail(B200SDR_INVALID_ARGUMENT, "gather is null");
   DeviceGuard guard(g->device);
-  for (unsigned s = 0; s < g->slabs; s++)
-    if (g->everSubmitted[s]) CUDA_OR_FAIL(cudaStreamWaitEvent(stream, g->drained[s], 0));
+  for (unsigned s = 0; s < g->slabs; s++) {
+    if (!g->everSubmitted[s]) continue;
+    if (g->mode == 1 && g->rank != 0) {  // delivered and released by rank 0
+      if (streamOps().wait(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(g->freeFlagOf(g->flags, s)), g->round[s],
+                           CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWaitValue32 failed");
+    } else {
+      CUDA_OR_FAIL(cudaStreamWaitEvent(stream, g->drained[s], 0));
+    }
+  }
   return B200SDR_OK;
 }
 

@@ -89,7 +89,10 @@ class Gather:
         N.check_status(N.lib.b200sdr_nccl_unique_id(buf), "b200sdr_nccl_unique_id")
         return buf.raw
 
-    def __init__(self, rank: int, world: int, floats_per_rank, slabs: int = 3, device: int = 0, unique_id: bytes | None = None):
+    NCCL, PEER = 0, 1
+
+    def __init__(self, rank: int, world: int, floats_per_rank, slabs: int = 3, device: int = 0, unique_id: bytes | None = None,
+                 mode: int = 0):
         import ctypes as C
         from . import _native as N
         self._N, self._C = N, C
@@ -103,6 +106,8 @@ class Gather:
         cfg.rank, cfg.world, cfg.slabs, cfg.cuda_device = rank, world, slabs, device
         cfg.floats_per_rank = self._counts
         cfg.nccl_unique_id = C.cast(self._id, C.c_void_p) if self._id is not None else None
+        cfg.mode = mode
+        self.mode = mode if world > 1 else 0
         handle = C.c_void_p()
         N.check_status(N.lib.b200sdr_gather_create(C.byref(cfg), C.byref(handle)), "b200sdr_gather_create")
         self._h = handle
@@ -117,6 +122,17 @@ class Gather:
             self.close()
         except Exception:
             pass
+
+    # peer mode: one exchange of IPC handles after construction (the caller all-gathers the blobs in rank order)
+    def export_blob(self) -> bytes:
+        size = self._N.lib.b200sdr_gather_exchange_size(self._h)
+        buf = self._C.create_string_buffer(size)
+        self._N.check_status(self._N.lib.b200sdr_gather_export(self._h, buf), "b200sdr_gather_export")
+        return buf.raw
+
+    def import_blobs(self, blobs: bytes) -> None:
+        buf = self._C.create_string_buffer(blobs, len(blobs))
+        self._N.check_status(self._N.lib.b200sdr_gather_import(self._h, buf), "b200sdr_gather_import")
 
     def slab(self, index: int):
         """This rank's part of slab `index` as a 1-D float32 torch tensor (a view of library-owned device memory)."""

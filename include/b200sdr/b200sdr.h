@@ -88,6 +88,13 @@ B200SDR_EXPORT b200sdr_status b200sdr_chain_segment(
     const b200sdr_chain* chain, size_t numAudio, size_t parts, size_t index, size_t* firstOutput, size_t* outputCount,
     size_t* firstInput, size_t* inputCount);
 
+/* The same with the outputs split in proportion to `weights` (HOST, `parts` positive numbers, e.g. each GPU's measured rate):
+ * on a box whose GPUs do not run at the same speed (power capping spreads them by a few per cent) the faster devices get the
+ * longer segments and all finish together.  weights == NULL: equal shares, as b200sdr_chain_segment. */
+B200SDR_EXPORT b200sdr_status b200sdr_chain_segment_weighted(
+    const b200sdr_chain* chain, size_t numAudio, size_t parts, const double* weights, size_t index, size_t* firstOutput,
+    size_t* outputCount, size_t* firstInput, size_t* inputCount);
+
 /* ---- device-resident processing (pointers are DEVICE pointers; async on `stream`) ---------------- */
 /* Stage K1: convert + mix + decimating FIR + demod in one kernel.  `numOutputs` demodulated floats
  * (AM/FM) or complex RF-FIR samples (NONE) are written to `output`.  `firstSampleIndex` is the absolute
@@ -198,12 +205,23 @@ typedef struct b200sdr_gather_config {
   uint32_t slabs;                 /* >= 2; 3 lets the main stream run ahead while two gathers drain */
   int32_t cuda_device;
   const size_t* floats_per_rank;  /* HOST, `world` entries: capacity of each rank's part of one slab, in floats */
-  const void* nccl_unique_id;     /* 128 bytes made by b200sdr_nccl_unique_id() on rank 0 and handed to every rank by the caller */
+  const void* nccl_unique_id;     /* NCCL mode: 128 bytes made by b200sdr_nccl_unique_id() on rank 0, handed to every rank by the caller */
+  uint32_t mode;                  /* B200SDR_GATHER_NCCL or B200SDR_GATHER_PEER */
+  uint32_t reserved;
 } b200sdr_gather_config;
+/* NCCL: one grouped ncclSend/ncclRecv per slab.  PEER: rank 0's gathered slabs are mapped into every rank of the box (CUDA IPC
+ * over NVLink / NVSwitch peer memory) and b200sdr_gather_slab() returns THAT memory, so the filter kernels store their audio
+ * straight into rank 0's buffer: the exchange costs no kernel and no SM; completion and reuse are sequenced by stream-ordered
+ * 32-bit flags.  Peer mode needs one exchange of handles after create: every rank exports a blob of
+ * b200sdr_gather_exchange_size() bytes, the caller all-gathers the blobs (rank order) and every rank imports them. */
+enum { B200SDR_GATHER_NCCL = 0, B200SDR_GATHER_PEER = 1 };
 typedef struct b200sdr_gather b200sdr_gather;
 B200SDR_EXPORT b200sdr_status b200sdr_nccl_unique_id(void* id128);
 B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config* config, b200sdr_gather** out);
 B200SDR_EXPORT void b200sdr_gather_destroy(b200sdr_gather* gather);
+B200SDR_EXPORT size_t b200sdr_gather_exchange_size(const b200sdr_gather* gather);
+B200SDR_EXPORT b200sdr_status b200sdr_gather_export(b200sdr_gather* gather, void* blob);
+B200SDR_EXPORT b200sdr_status b200sdr_gather_import(b200sdr_gather* gather, const void* blobsOfAllRanks);
 /* DEVICE pointer of this rank's part of slab `slab` (floats_per_rank[rank] floats): the kernels write their audio here. */
 B200SDR_EXPORT float* b200sdr_gather_slab(b200sdr_gather* gather, uint32_t slab);
 /* Before writing into a slab again: `stream` waits until the slab's previous gather has read it. */

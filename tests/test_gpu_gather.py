@@ -97,3 +97,34 @@ def test_two_ranks_shard_the_chain_bit_exactly(sdr):
     assert not errors, errors
     assert results["nccl"] >= 20000
     assert torch.equal(results["audio"].view(torch.int32), whole.view(torch.int32))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in the box (gpurun --gpus 2)")
+def test_peer_mode_gather_two_processes():
+    """Peer mode needs one process per GPU (CUDA IPC): two ranks under torchrun, weighted (unequal) time segments, the chain kernel
+    storing straight into rank 0's slabs over NVLink, seven rounds over two slabs; the gathered audio equals the one-device run
+    bit for bit (tests/gather_peer_worker.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(root, "tests", "gather_peer_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert res.returncode == 0 and "PEER_GATHER_OK" in res.stdout, (res.stdout + res.stderr)[-3000:]
+
+
+def test_weighted_segments_tile_the_outputs(sdr):
+    fs = 19.2e6
+    chain = sdr.Chain(fs, -1.234e6, sdr.taps.lowpass(101, 0.45 * fs / 40, fs), 40, sdr.FM, fm_gain=0.1,
+                      audio_taps=sdr.taps.lowpass(129, 0.45 * 48e3, fs / 40), audio_decim=10)
+    for weights in ([1.0, 1.0, 1.0], [0.97, 1.03, 1.0, 1.01, 0.99, 1.0, 1.02, 0.98], [5.0, 1.0]):
+        segs = [chain.segment_weighted(100003, weights, i) for i in range(len(weights))]
+        assert segs[0][0] == 0 and segs[-1][0] + segs[-1][1] == 100003
+        for a, b in zip(segs, segs[1:]):
+            assert a[0] + a[1] == b[0]
+        for (first, count, i0, icnt), w in zip(segs, weights):
+            assert i0 == first * chain.stride and icnt == (count - 1) * chain.stride + chain.window
+            assert abs(count - 100003 * w / sum(weights)) <= 1.0
+    equal = [chain.segment_weighted(977, [1.0] * 4, i)[1] for i in range(4)]
+    assert sum(equal) == 977 and max(equal) - min(equal) <= 1
