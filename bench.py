@@ -92,6 +92,14 @@ def workload(name: str):
                 t2=taps.lowpass(273, 0.45 * 48e3, FS / 80), d2=5)
 
 
+GATHER_TRANSPORT = {
+    0: "NCCL grouped send/recv on a side stream",
+    1: "peer memory: the kernels store into rank 0's slabs over NVLink (CUDA IPC), stream-ordered 32-bit flags",
+    2: "peer memory: a copy engine moves each rank's local slab into rank 0's slabs over NVLink (CUDA IPC) on a side stream, "
+       "stream-ordered 32-bit flags",
+}
+
+
 def config_dict(wl, log2_samples, extra=None):
     """`workload` names the chain (identical in both arms); the block one step processes is a separate key, because the CPU arm
     runs a bounded sample of the GPU arm's block (the metric is a rate)."""
@@ -307,15 +315,18 @@ class Ctx:
                 os.close(saved_stdout)
 
     def make_gather(self, floats_per_rank, slabs=3):
-        """b200sdr_gather over all ranks.  Peer mode first (rank 0's slabs mapped into every rank over NVLink: the kernels store
-        their audio straight into them; the IPC handles travel through torch.distributed), NCCL send/recv if that is unavailable
-        or BENCH_GATHER=nccl (the 128-byte NCCL id then travels from rank 0 the same way)."""
+        """b200sdr_gather over all ranks.  Peer memory first (rank 0's slabs mapped into every rank over NVLink; a copy engine
+        moves each rank's local slab into them, or with BENCH_GATHER=store the kernels store their audio straight into them; the
+        IPC handles travel through torch.distributed), NCCL send/recv if that is unavailable or BENCH_GATHER=nccl (the 128-byte
+        NCCL id then travels from rank 0 the same way)."""
         from cuda_sdr_b200 import sharding
         torch, dist = self.torch, self.dist
-        if self.world > 1 and os.environ.get("BENCH_GATHER", "peer") == "peer":
+        want = os.environ.get("BENCH_GATHER", "copy")  # copy: local slab + copy engine (default); store (= peer): kernels store remotely
+        if self.world > 1 and want in ("copy", "store", "peer"):
             g, ok = None, 1
             try:
-                g = sharding.Gather(self.rank, self.world, floats_per_rank, slabs=slabs, device=self.local_rank, mode=sharding.Gather.PEER)
+                g = sharding.Gather(self.rank, self.world, floats_per_rank, slabs=slabs, device=self.local_rank,
+                                    mode=sharding.Gather.PEER_COPY if want == "copy" else sharding.Gather.PEER)
                 blob = g.export_blob()
             except Exception as e:
                 ok, blob = 0, b""
@@ -462,9 +473,10 @@ def run_chain(args, ctx):
     x = x_all[: 2 * n]
     demod = torch.empty(n_demod + (n_demod >> 3), dtype=torch.float32, device=dev)
     first_index = rank * n  # absolute sample index of the segment (mixer phase)
-    # Audio of GATHER_EVERY consecutive steps is collected in one of three slabs; a full slab is gathered to rank 0 by ONE grouped
-    # NCCL send/recv on the library's side stream while the next slabs fill.  The cadence follows the run length so that at most
-    # ~1/4 of the audio can still be in flight when the last kernel ends.
+    # Audio of up to `ge` consecutive steps is collected in one of three slabs; a submitted slab travels to rank 0 on the library's
+    # side stream while the next slabs fill.  Slabs are long in the steady state (every submit puts an event between two launches
+    # and so costs that pair its programmatic overlap) and shrink towards the end of a run (slab_schedule), so that only ONE step of
+    # audio is still to be moved when the last kernel ends -- a streaming application that knows its end flushes the same way.
     ge = int(os.environ.get("BENCH_GATHER_EVERY", "0")) or max(1, min(32, args.steps // 4))
     slabs = 3
     step_no = [0]
@@ -475,7 +487,7 @@ def run_chain(args, ctx):
     sampler = ClockSampler(ctx.local_rank)
     sampler.start()
     # warm-up, part 1: the local kernel alone until the clocks are up (time-based, so NO communication in it -- ranks would run
-    # different counts).  Its rate is also what the balanced partition is computed from.
+    # different counts)
     scratch_out = torch.empty(n_audio + (n_audio >> 3), dtype=torch.float32, device=dev)
     extra = 0
     torch.cuda.synchronize()
@@ -486,65 +498,90 @@ def run_chain(args, ctx):
         if extra % 16 == 0:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
-    my_rate = extra / max(time.perf_counter() - t_warm, 1e-9)
     # Partition of the stream over the ranks.  The total work of a step is world * 2^log2_block samples whatever the split; with
     # --no-balance every rank takes exactly its 2^log2_block, otherwise b200sdr_chain_segment_weighted cuts the world-wide run of
-    # audio outputs in proportion to each GPU's measured rate (power-capped GPUs of one box differ by a few per cent, and a step
-    # ends with the slowest), and every rank reads the input segment its outputs need.
-    counts_audio = [n_audio] * world
-    my_in, my_first_in, my_audio = n, first_index, n_audio
-    shares = None
-    if balance:
-        rates = [r if r > 0 else 1.0 for r in ctx.gather_objects(my_rate)]
-        mean = sum(rates) / world
-        weights = [min(max(r / mean, 0.90), 1.10) for r in rates]  # stay inside the allocation whatever a noisy measurement says
-        total_audio = chain.counts(world * n)[2]
-        segs = [chain.segment_weighted(total_audio, weights, r) for r in range(world)]
-        counts_audio = [sg[1] for sg in segs]
-        _, my_audio, my_first_in, my_in = segs[rank]
-        assert my_in <= n_alloc and my_audio <= scratch_out.numel()
-        x = x_all[: 2 * my_in]
-        shares = [sg[3] / n for sg in segs]
-    gather = ctx.make_gather([ge * c for c in counts_audio], slabs) if world > 1 else None
-    if gather is not None:
-        views = [gather.slab(s)[: ge * my_audio].view(ge, my_audio) for s in range(slabs)]
-    else:
-        views = [torch.empty(ge, my_audio, dtype=torch.float32, device=dev) for _ in range(slabs)]
+    # audio outputs in proportion to each GPU's measured rate (power-capped GPUs of one box differ by a few per cent, rank 0 also
+    # absorbs the other ranks' audio, and a step ends with the slowest), and every rank reads the input segment its outputs need.
+    part = {"audio": n_audio, "first": first_index, "in": n, "counts": [n_audio] * world, "x": x, "views": None}
+    cap_audio = n_audio + (n_audio >> 3)
+    gather = ctx.make_gather([ge * cap_audio] * world, slabs) if world > 1 else None
 
-    def step(i=None, last=False):
-        k = step_no[0]
-        step_no[0] += 1
-        slab, slot = (k // ge) % slabs, k % ge
-        if gather is not None and slot == 0:
-            gather.acquire(slab)  # this slab's previous gather has drained
-        if i is not None and not fused:
-            k_events[i][0].record()
-        # fused: ONE kernel; else K1 + K2.  Exactly my_audio outputs of the segment that starts at absolute sample my_first_in.
-        got = chain.run(x, my_audio, my_first_in, out=views[slab][slot], scratch=demod, n_in=my_in)
-        if i is not None and not fused:
-            k_events[i][1].record()
-        assert got.numel() == my_audio
-        if slot == ge - 1 or last:
+    def set_partition(segs):
+        if segs is not None:
+            part["counts"] = [sg[1] for sg in segs]
+            _, part["audio"], part["first"], part["in"] = segs[rank]
+            assert part["in"] <= n_alloc and part["audio"] <= cap_audio
+            part["x"] = x_all[: 2 * part["in"]]
+        a = part["audio"]
+        if gather is not None:
+            part["views"] = [gather.slab(s)[: ge * a].view(ge, a) for s in range(slabs)]
+        else:
+            part["views"] = [torch.empty(ge, a, dtype=torch.float32, device=dev) for _ in range(slabs)]
+
+    set_partition(None)
+
+    def slab_schedule(nsteps):
+        sizes, left = [], nsteps
+        while left > 0:
+            sizes.append(min(ge, max(1, left // 2)))
+            left -= sizes[-1]
+        return sizes
+
+    def run_steps(nsteps, events=None, timed=False):
+        """nsteps steps of the chain, slab by slab; events: one (start, end) pair per step around the kernel(s)."""
+        i = 0
+        for size in slab_schedule(nsteps):
+            slab = step_no[0] % slabs
+            step_no[0] += 1
             if gather is not None:
-                gather.submit(slab, [(slot + 1) * c for c in counts_audio])
-            step_no[0] += ge - 1 - slot  # a partial slab at the end of a phase: start the next phase on a fresh slab
+                gather.acquire(slab)  # this slab's previous gather has drained
+            for slot in range(size):
+                ev = events[i] if events is not None else (k_events[i] if timed and not fused else None)
+                if ev is not None:
+                    ev[0].record()
+                # fused: ONE kernel; else K1 + K2.  Exactly part["audio"] outputs of the segment that starts at sample part["first"].
+                got = chain.run(part["x"], part["audio"], part["first"], out=part["views"][slab][slot], scratch=demod, n_in=part["in"])
+                if ev is not None:
+                    ev[1].record()
+                i += 1
+            assert got.numel() == part["audio"]
+            if gather is not None:
+                gather.submit(slab, [size * c for c in part["counts"]])
 
     def quiesce():
         if gather is not None:
             gather.finish()
         ctx.barrier()
 
+    # warm-up, part 1b (N > 1, balanced): the rate of every GPU UNDER THE LOAD OF THE RUN -- all ranks stepping in lockstep with equal
+    # segments, the gather active (rank 0 absorbing the others' audio) -- from CUDA events around each kernel; the median of
+    # `cal` steps.  A rate measured on each GPU alone misjudges exactly the rank that matters (rank 0).
+    shares = rates = None
+    if balance:
+        cal = 32
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(cal)]
+        quiesce()
+        run_steps(cal, events=evs)
+        quiesce()
+        my_rate = 1.0 / max(statistics.median(a.elapsed_time(b) for a, b in evs), 1e-6)  # steps per millisecond
+        rates = [r if r > 0 else 1.0 for r in ctx.gather_objects(my_rate)]
+        mean = sum(rates) / world
+        weights = [min(max(r / mean, 0.90), 1.10) for r in rates]  # stay inside the allocation whatever a noisy measurement says
+        total_audio = chain.counts(world * n)[2]
+        segs = [chain.segment_weighted(total_audio, weights, r) for r in range(world)]
+        set_partition(segs)
+        shares = [sg[3] / n for sg in segs]
+        extra += cal
+    my_in, my_first_in, my_audio = part["in"], part["first"], part["audio"]
     # warm-up, part 2: max(W, 3) complete steps including the gather, in lockstep on every rank
     n_warm = max(args.warmup, 3)
-    for w in range(n_warm):
-        step(last=(w == n_warm - 1))
+    run_steps(n_warm)
     quiesce()
     launches0 = sdr._native.launch_count()
     t_start, t_kernels, t_end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     quiesce()
     t_start.record()
-    for i in range(args.steps):
-        step(i, last=(i == args.steps - 1))
+    run_steps(args.steps, timed=True)
     t_kernels.record()  # the last kernel of this rank
     if gather is not None:
         gather.finish()  # the gathers are part of the timed region
@@ -623,8 +660,8 @@ def run_chain(args, ctx):
                 "kernel_variant": chain.variant,
                 "l2": f"input block {2 * n >> 20} MiB per step exceeds the 126 MB L2; no flush between iterations",
                 "parallelism": ("overlapped time segments, one per GPU" + (", lengths balanced by measured GPU rate" if balance else "") +
-                                ", no collective on the filter path; b200sdr_gather (libb200sdr.so): one "
-                                f"grouped NCCL send/recv per {ge} steps of audio to rank 0 on a side stream, 3 slabs") if world > 1 else
+                                f", no collective on the filter path; b200sdr_gather (libb200sdr.so): up to {ge} steps of audio per slab "
+                                f"to rank 0, 3 slabs; {GATHER_TRANSPORT[gather_mode]}") if world > 1 else
                                "single GPU"}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": kernel_name, "kernel_ms": k_ms,
@@ -633,17 +670,17 @@ def run_chain(args, ctx):
             "per_rank": per_rank, "comm_exposed_ms": max(p["comm_exposed_ms"] for p in per_rank),
         }
         if gstats:
-            line["gather"] = {"transport": "peer memory (kernels store into rank 0's slabs over NVLink; stream-ordered flags)" if gather_mode == 1
-                              else "NCCL grouped send/recv on a side stream",
-                              "steps_per_gather": ge, "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
-                              "bytes_into_rank0_per_step": 4 * sum(counts_audio[1:])}
+            line["gather"] = {"transport": GATHER_TRANSPORT[gather_mode],
+                              "steps_per_slab": slab_schedule(args.steps), "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
+                              "bytes_into_rank0_per_step": 4 * sum(part["counts"][1:])}
         if shares is not None:
             line["balance"] = {"what": "time segments in proportion to each GPU's rate measured in the warm-up (b200sdr_chain_segment_weighted); "
                                        "the step's total stays n_gpus * samples_per_gpu_per_step",
-                               "segment_samples_over_average": shares, "warmup_steps_per_second": rates}
+                               "segment_samples_over_average": shares, "calibration_steps_per_ms": rates}
         if e2e:
             line["e2e"] = e2e
-    del x, x_all, demod, views, scratch_out
+    part.clear()
+    del x, x_all, demod, scratch_out
     if gather is not None:
         gather.close()
     torch.cuda.empty_cache()
@@ -727,6 +764,10 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
         else:
             ctx.barrier()
 
+    # the clock sampler polls every 50 ms and the timed region lasts a few milliseconds: it runs from the warm-up (the same kernels
+    # back to back) through the timed region
+    sampler = ClockSampler(ctx.local_rank)
+    sampler.start()
     t_warm = time.perf_counter()
     extra = 0
     while time.perf_counter() - t_warm < min(args.warmup_seconds, 0.3):
@@ -737,8 +778,6 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
     for _ in range(n_warm):
         step()
     quiesce()
-    sampler = ClockSampler(ctx.local_rank)
-    sampler.start()
     launches0 = sdr._native.launch_count()
     t0, tk, t1e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     quiesce()
@@ -802,7 +841,8 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
                        "route": ch.variant,
                        "parallelism": (("overlapped time segments of the wideband stream, every GPU produces all channels for its share of the "
                                         "audio outputs" if by_time else "channels interleaved over the GPUs (c mod G), input replicated") +
-                                       "; b200sdr_gather: one grouped NCCL send/recv per step of audio to rank 0 on a side stream, 3 slabs")
+                                       "; b200sdr_gather: one slab of audio per step to rank 0, 3 slabs; " +
+                                       GATHER_TRANSPORT[gather.mode if gather is not None else 0])
                        if world > 1 else "single GPU",
                        "l2": f"input block {2 * n >> 20} MiB exceeds the 126 MB L2"},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks,
@@ -811,7 +851,7 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
             rec["per_rank"] = per_rank
             rec["comm_exposed_ms"] = max(p["comm_exposed_ms"] for p in per_rank)
             rec["gather"] = {"bytes_into_rank0_per_step": 4 * sum(floats[1:]), "slabs": slabs, "calls": gather.stats()["gathers"],
-                             "transport": "peer memory" if gather.mode == 1 else "NCCL send/recv"}
+                             "transport": GATHER_TRANSPORT[gather.mode]}
     del x, x_mine, scratch, outs
     if gather is not None:
         gather.close()

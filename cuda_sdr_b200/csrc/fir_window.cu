@@ -113,11 +113,20 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
     }
   }
 
+  // Outputs leave through shared memory so that every store instruction of a warp covers one contiguous run (thread-major
+  // stores would touch 4 bytes of 32 different sectors per instruction: harmless in the local L2, which merges them, but each of
+  // them is a separate small write when `out` is a peer GPU's memory over NVLink -- the multi-GPU channelizer).
+  __syncthreads();
+  Elem* sOut = sX;  // BO + BO / R elements <= one staged row
+#pragma unroll
+  for (int r = 0; r < kWinR; r++) sOut[tid * (kWinR + 1) + r] = acc[r];
+  __syncthreads();
   Elem* out = static_cast<Elem*>(prm.out) + blockIdx.y * prm.outBatchStride;
 #pragma unroll
-  for (int r = 0; r < kWinR; r++) {
-    const unsigned long long k = k0 + static_cast<unsigned long long>(tid) * kWinR + r;
-    if (k < prm.nOut) out[k] = acc[r];
+  for (int j = 0; j < kWinR; j++) {
+    const unsigned o = j * kWinThreads + tid;
+    const unsigned long long k = k0 + o;
+    if (k < prm.nOut) out[k] = sOut[winPadded<kWinR>(o)];
   }
 }
 

@@ -10,16 +10,20 @@
 // NCCL is bound at run time (dlopen "libnccl.so.2"): libb200sdr.so has no link-time dependency on it, single-GPU users
 // never load it, and inside a process that already carries NCCL (PyTorch) the same library instance is used.
 //
-// Two transports:
-//   mode 0 (NCCL)  one grouped ncclSend/ncclRecv per slab on the side stream.
-//   mode 1 (peer)  the gathered slabs of rank 0 are mapped into every rank (CUDA IPC over NVLink / NVSwitch peer memory) and
-//                  b200sdr_gather_slab() hands the kernels THAT memory: the filter kernels store their audio straight into
-//                  rank 0's buffer while they compute, so the exchange costs no kernel, no SM and no extra pass over the data.
-//                  Completion and buffer reuse are sequenced by 32-bit flags written / awaited in stream order
-//                  (cuStreamWriteValue32 / cuStreamWaitValue32): rank r -> rank 0 "slab s holds round n of rank r",
-//                  rank 0 -> rank r "slab s is free again".  Measured on 8 B200: with NCCL's receive kernels on rank 0 the
-//                  persistent filter kernel loses its second CTA per SM while a gather runs (3x per step in a 20-step run);
-//                  with peer stores the step time of rank 0 equals the others'.
+// Three transports:
+//   mode 0 (NCCL)        one grouped ncclSend/ncclRecv per slab on the side stream.
+//   mode 1 (peer store)  the gathered slabs of rank 0 are mapped into every rank (CUDA IPC over NVLink / NVSwitch peer memory) and
+//                        b200sdr_gather_slab() hands the kernels THAT memory: the filter kernels store their audio straight into
+//                        rank 0's buffer while they compute -- no kernel, no SM and no extra pass over the data.
+//   mode 2 (peer copy)   the kernels write a LOCAL slab; the side stream moves it into rank 0's mapped slab with one
+//                        cudaMemcpyAsync, i.e. a copy engine over NVLink -- no SM either, one extra read of the (decimated) audio.
+//   Modes 1 and 2 sequence completion and buffer reuse with 32-bit flags written / awaited in stream order
+//   (cuStreamWriteValue32 / cuStreamWaitValue32): rank r -> rank 0 "slab s holds round n of rank r", rank 0 -> rank r "slab s is
+//   free again".
+// Measured on 8 B200 (profiles/README.md, round 2): NCCL's send / receive kernels take SMs from the persistent filter kernel while a
+// gather runs; peer stores leave the SMs alone but every kernel then ends with its remote stores still in flight (+5 % per C2
+// step) and a bursty writer (the channelizer's audio kernel: 130 MB into rank 0 within 0.15 ms) is bound by rank 0's NVLink
+// ingress; the copy engine spreads the same bytes over the whole next step.
 #include <b200sdr/b200sdr.h>
 
 #include <cuda.h>  // CUstream / CUdeviceptr / CUresult (types only; entry points are fetched at run time)
@@ -144,8 +148,9 @@ struct b200sdr_gather {
   std::vector<cudaEvent_t> filled, drained;
   std::vector<char> everSubmitted;
   uint64_t gathers = 0, floatsMoved = 0;
-  // peer mode
+  // peer modes (1: kernels store into rank 0's slabs; 2: local slab + copy engine)
   int mode = 0;
+  bool peerAny() const { return mode != 0; }
   bool imported = false;
   uint32_t* flags = nullptr;                 // this rank's flag block: [slabs][world] "filled" (used on rank 0) + [slabs] "free"
   std::vector<float*> remoteSlab;            // rank != 0: rank 0's gathered slabs mapped here
@@ -194,8 +199,8 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config*
   if (cfg->struct_size != sizeof(b200sdr_gather_config)) return chainFail(B200SDR_INVALID_ARGUMENT, "struct_size mismatch");
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world || cfg->slabs < 2 || !cfg->floats_per_rank)
     return chainFail(B200SDR_INVALID_ARGUMENT, "need 0 <= rank < world, slabs >= 2 and floats_per_rank");
-  if (cfg->mode > B200SDR_GATHER_PEER) return chainFail(B200SDR_INVALID_ARGUMENT, "unknown gather mode");
-  const bool peer = cfg->mode == B200SDR_GATHER_PEER && cfg->world > 1;
+  if (cfg->mode > B200SDR_GATHER_PEER_COPY) return chainFail(B200SDR_INVALID_ARGUMENT, "unknown gather mode");
+  const bool peer = cfg->mode != B200SDR_GATHER_NCCL && cfg->world > 1;
   if (cfg->world > 1 && !peer && !cfg->nccl_unique_id) return chainFail(B200SDR_INVALID_ARGUMENT, "nccl_unique_id is required when world > 1");
   if (peer && (!streamOps().write || !streamOps().wait)) return chainFail(B200SDR_RUNTIME_ERROR, "the driver lacks cuStreamWriteValue32 / cuStreamWaitValue32");
   b200sdr_gather* g = new (std::nothrow) b200sdr_gather();
@@ -204,7 +209,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config*
   g->rank = cfg->rank;
   g->world = cfg->world;
   g->slabs = cfg->slabs;
-  g->mode = peer ? 1 : 0;
+  g->mode = peer ? static_cast<int>(cfg->mode) : 0;
   g->round.assign(cfg->slabs, 0u);
   g->floatsOf.assign(cfg->floats_per_rank, cfg->floats_per_rank + cfg->world);
   g->offsetOf.resize(cfg->world);
@@ -261,14 +266,15 @@ B200SDR_EXPORT float* b200sdr_gather_slab(b200sdr_gather* g, uint32_t slab) {
   if (!g || slab >= g->slabs) return nullptr;
   if (g->mode == 0) return g->local[slab];
   if (!g->imported) return nullptr;  // the peer mappings exist after b200sdr_gather_import
+  if (g->mode == 2 && g->rank != 0) return g->local[slab];  // moved by the copy engine at submit
   return (g->rank == 0 ? g->gathered[slab] : g->remoteSlab[slab]) + g->offsetOf[g->rank];  // rank 0's memory, this rank's part
 }
 
-B200SDR_EXPORT size_t b200sdr_gather_exchange_size(const b200sdr_gather* g) { return g && g->mode == 1 ? exchangeBytes(g) : 0; }
+B200SDR_EXPORT size_t b200sdr_gather_exchange_size(const b200sdr_gather* g) { return g && g->peerAny() ? exchangeBytes(g) : 0; }
 
 // This rank's blob: the IPC handles of rank 0's gathered slabs (zero elsewhere) and of this rank's flag block.
 B200SDR_EXPORT b200sdr_status b200sdr_gather_export(b200sdr_gather* g, void* blob) {
-  if (!g || !blob || g->mode != 1) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
+  if (!g || !blob || !g->peerAny()) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
   DeviceGuard guard(g->device);
   unsigned char* out = static_cast<unsigned char*>(blob);
   std::memset(out, 0, exchangeBytes(g));
@@ -286,7 +292,7 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_export(b200sdr_gather* g, void* blo
 
 // blobs: `world` blobs of b200sdr_gather_exchange_size() bytes each, in rank order (gathered by the caller's transport)
 B200SDR_EXPORT b200sdr_status b200sdr_gather_import(b200sdr_gather* g, const void* blobs) {
-  if (!g || !blobs || g->mode != 1) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
+  if (!g || !blobs || !g->peerAny()) return chainFail(B200SDR_INVALID_ARGUMENT, "not a peer-mode gather");
   if (g->imported) return B200SDR_OK;
   DeviceGuard guard(g->device);
   const unsigned char* in = static_cast<const unsigned char*>(blobs);
@@ -339,7 +345,27 @@ B200SDR_EXPORT b200sdr_status b200sdr_gather_submit(b200sdr_gather* g, uint32_t 
   const size_t* counts = floatsPerRank ? floatsPerRank : g->floatsOf.data();
   for (int r = 0; r < g->world; r++)
     if (counts[r] > g->floatsOf[r]) return chainFail(B200SDR_OUT_OF_RANGE, "more floats than the slab holds");
-  if (g->mode == 1) {
+  if (g->mode == 2 && g->rank != 0) {
+    if (!g->imported) return chainFail(B200SDR_INVALID_STATE, "b200sdr_gather_import has not been called");
+    const uint32_t round = ++g->round[slab];
+    CUDA_OR_FAIL(cudaEventRecord(g->filled[slab], stream));
+    CUDA_OR_FAIL(cudaStreamWaitEvent(g->side, g->filled[slab], 0));
+    // rank 0 has released the previous round of its slab (a flag in THIS rank's memory); back-pressure stays on the side stream
+    if (round > 1 && streamOps().wait(reinterpret_cast<CUstream>(g->side), reinterpret_cast<CUdeviceptr>(g->freeFlagOf(g->flags, slab)), round - 1,
+                                      CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+      return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWaitValue32 failed");
+    if (counts[g->rank])  // a copy engine moves the slab over NVLink into rank 0's memory
+      CUDA_OR_FAIL(cudaMemcpyAsync(g->remoteSlab[slab] + g->offsetOf[g->rank], g->local[slab], sizeof(float) * counts[g->rank], cudaMemcpyDefault, g->side));
+    if (streamOps().write(reinterpret_cast<CUstream>(g->side), reinterpret_cast<CUdeviceptr>(g->remoteFlags[0] + slab * g->world + g->rank), round, 0) !=
+        CUDA_SUCCESS)
+      return chainFail(B200SDR_RUNTIME_ERROR, "cuStreamWriteValue32 failed");
+    CUDA_OR_FAIL(cudaEventRecord(g->drained[slab], g->side));  // the local slab may be written again
+    g->everSubmitted[slab] = 1;
+    g->gathers++;
+    g->floatsMoved += counts[g->rank];
+    return B200SDR_OK;
+  }
+  if (g->peerAny()) {
     if (!g->imported) return chainFail(B200SDR_INVALID_STATE, "b200sdr_gather_import has not been called");
     const uint32_t round = ++g->round[slab];
     // "slab holds round `round` of this rank": a flag in RANK 0's memory, written behind the kernels that stored the audio there

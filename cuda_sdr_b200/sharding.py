@@ -89,7 +89,7 @@ class Gather:
         N.check_status(N.lib.b200sdr_nccl_unique_id(buf), "b200sdr_nccl_unique_id")
         return buf.raw
 
-    NCCL, PEER = 0, 1
+    NCCL, PEER, PEER_COPY = 0, 1, 2
 
     def __init__(self, rank: int, world: int, floats_per_rank, slabs: int = 3, device: int = 0, unique_id: bytes | None = None,
                  mode: int = 0):

@@ -206,15 +206,17 @@ typedef struct b200sdr_gather_config {
   int32_t cuda_device;
   const size_t* floats_per_rank;  /* HOST, `world` entries: capacity of each rank's part of one slab, in floats */
   const void* nccl_unique_id;     /* NCCL mode: 128 bytes made by b200sdr_nccl_unique_id() on rank 0, handed to every rank by the caller */
-  uint32_t mode;                  /* B200SDR_GATHER_NCCL or B200SDR_GATHER_PEER */
+  uint32_t mode;                  /* B200SDR_GATHER_NCCL, B200SDR_GATHER_PEER or B200SDR_GATHER_PEER_COPY */
   uint32_t reserved;
 } b200sdr_gather_config;
 /* NCCL: one grouped ncclSend/ncclRecv per slab.  PEER: rank 0's gathered slabs are mapped into every rank of the box (CUDA IPC
  * over NVLink / NVSwitch peer memory) and b200sdr_gather_slab() returns THAT memory, so the filter kernels store their audio
- * straight into rank 0's buffer: the exchange costs no kernel and no SM; completion and reuse are sequenced by stream-ordered
- * 32-bit flags.  Peer mode needs one exchange of handles after create: every rank exports a blob of
- * b200sdr_gather_exchange_size() bytes, the caller all-gathers the blobs (rank order) and every rank imports them. */
-enum { B200SDR_GATHER_NCCL = 0, B200SDR_GATHER_PEER = 1 };
+ * straight into rank 0's buffer.  PEER_COPY: the same mapping, but b200sdr_gather_slab() returns a local slab and
+ * b200sdr_gather_submit() moves it into rank 0's memory with a copy engine (cudaMemcpyAsync over NVLink) on the side stream.
+ * Neither peer mode costs a kernel or an SM; completion and reuse are sequenced by stream-ordered 32-bit flags.  The peer modes
+ * need one exchange of handles after create: every rank exports a blob of b200sdr_gather_exchange_size() bytes, the caller
+ * all-gathers the blobs (rank order) and every rank imports them. */
+enum { B200SDR_GATHER_NCCL = 0, B200SDR_GATHER_PEER = 1, B200SDR_GATHER_PEER_COPY = 2 };
 typedef struct b200sdr_gather b200sdr_gather;
 B200SDR_EXPORT b200sdr_status b200sdr_nccl_unique_id(void* id128);
 B200SDR_EXPORT b200sdr_status b200sdr_gather_create(const b200sdr_gather_config* config, b200sdr_gather** out);

@@ -1,6 +1,7 @@
 """Worker of tests/test_gpu_gather.py::test_peer_mode_gather_two_processes (run under torchrun, one process per GPU): every rank
 runs its time segment of one stream with the chain kernel STORING INTO RANK 0'S MEMORY (b200sdr_gather, peer mode: CUDA IPC over
-NVLink, stream-ordered flags); rank 0 checks the gathered audio against its own single-device run, bit for bit."""
+NVLink, stream-ordered flags) or, with argument "copy", into a local slab that a copy engine moves there; rank 0 checks the
+gathered audio against its own single-device run, bit for bit."""
 import os
 import sys
 
@@ -28,7 +29,7 @@ def main():
     weights = [1.0 + 0.07 * r for r in range(world)]  # unequal shares: the balanced partition
     segs = [chain.segment_weighted(n_audio, weights, r) for r in range(world)]
     assert segs[0][0] == 0 and sum(s[1] for s in segs) == n_audio and all(segs[i][0] + segs[i][1] == segs[i + 1][0] for i in range(world - 1))
-    g = sharding.Gather(rank, world, [s[1] for s in segs], slabs=2, device=local, mode=sharding.Gather.PEER)
+    g = sharding.Gather(rank, world, [s[1] for s in segs], slabs=2, device=local, mode=sharding.Gather.PEER_COPY if sys.argv[1:] == ["copy"] else sharding.Gather.PEER)
     blobs = [None] * world
     dist.all_gather_object(blobs, g.export_blob())
     g.import_blobs(b"".join(blobs))

@@ -100,16 +100,17 @@ def test_two_ranks_shard_the_chain_bit_exactly(sdr):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in the box (gpurun --gpus 2)")
-def test_peer_mode_gather_two_processes():
-    """Peer mode needs one process per GPU (CUDA IPC): two ranks under torchrun, weighted (unequal) time segments, the chain kernel
-    storing straight into rank 0's slabs over NVLink, seven rounds over two slabs; the gathered audio equals the one-device run
-    bit for bit (tests/gather_peer_worker.py)."""
+@pytest.mark.parametrize("transport", ["store", "copy"])
+def test_peer_mode_gather_two_processes(transport):
+    """The peer modes need one process per GPU (CUDA IPC): two ranks under torchrun, weighted (unequal) time segments, the chain
+    kernel storing straight into rank 0's slabs over NVLink ("store") or into a local slab moved there by a copy engine ("copy"),
+    seven rounds over two slabs; the gathered audio equals the one-device run bit for bit (tests/gather_peer_worker.py)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(root, "tests", "gather_peer_worker.py")]
+           os.path.join(root, "tests", "gather_peer_worker.py"), transport]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert res.returncode == 0 and "PEER_GATHER_OK" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
