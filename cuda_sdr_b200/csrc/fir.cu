@@ -99,6 +99,29 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
     k<<<static_cast<unsigned>(blocks), kRowsThreads, route.smemBytes, stream>>>(prm);
     return launchStatus();
   }
+  // 8 < M <= 32 on long rows (D >= 16; complex float data, real taps, no mixer): the rows kernel with 16 or 32 partial sums per
+  // row.  Few outputs per input sample, so the cell is HBM-bound and wants the tile streamed ONCE by TMA; the window kernel would
+  // walk the D phases in D / 4 strided passes.
+  if (elem == kElemComplex && !tapsComplex && !mix && route.M > 8 && route.M <= 32 && prm.D >= 16 && prm.D % 2 == 0 &&
+      (reinterpret_cast<uintptr_t>(prm.in) & 15u) == 0 && envInt("B200SDR_NO_WIDE_ROWS", 0) == 0) {
+    const unsigned MP = route.M <= 16 ? 16u : 32u, fm = prm.mod == kModFm ? 1u : 0u;
+    const unsigned rpt = (MP == 16 && 2u * kRowsThreads * rowsRowStride(prm.D, 8) <= 64u * 1024u) ? 2u : 1u;
+    const unsigned rowsPerTile = rpt * kRowsThreads;
+    const RowsSmem lay = rowsSmemLayout(prm.D, MP, route.M, rowsPerTile, 8, fm != 0);
+    if (lay.total <= 100u * 1024u) {
+      prm.rowsPerTile = rowsPerTile;
+      prm.outPerTile = rowsPerTile - (route.M - 1) - fm;
+      const Kernel k = kRowsCf32PlainWide[MP == 16 ? (rpt == 2 ? 1 : 0) : 2];
+      if (lay.total > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+        if (e != cudaSuccess) return e;
+      }
+      const unsigned long long blocks = (prm.nOut + prm.outPerTile - 1) / prm.outPerTile;
+      if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+      k<<<static_cast<unsigned>(blocks), kRowsThreads, lay.total, stream>>>(prm);
+      return launchStatus();
+    }
+  }
   if (envInt("B200SDR_NO_WINDOW", 0) == 0 && windowEligible(elem, tapsComplex, mix, prm)) return launchWindow(elem, prm, stream);
   const unsigned outPerBlock = prm.mod == kModFm ? kDirectThreads - 1 : kDirectThreads;
   const unsigned long long blocks = (prm.nOut + outPerBlock - 1) / outPerBlock;

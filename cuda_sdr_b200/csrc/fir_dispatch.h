@@ -33,6 +33,6 @@ cudaError_t launchWindowBatched(int elem, FirParams prm, unsigned batch, cudaStr
 constexpr unsigned rowsRptHigh(unsigned MP) { return MP <= 4 ? 4u : 2u; }
 
 using FirKernel = void (*)(const FirParams);
-extern const FirKernel kRowsInt8Mix[16], kRowsInt8Plain[16], kRowsCf32Mix[16], kRowsCf32Plain[16];
+extern const FirKernel kRowsInt8Mix[16], kRowsInt8Plain[16], kRowsCf32Mix[16], kRowsCf32Plain[16], kRowsCf32PlainWide[3];
 
 }  // namespace b200sdr

@@ -130,7 +130,7 @@ struct ElemTraits<kElemComplex> {
 constexpr int kRowsThreads = 128;
 
 // Row stride (floats) of the transposed tap table hT[p][.] for MP partial sums: next power of two.
-__host__ __device__ constexpr int tapStride(int MP) { return MP <= 1 ? 1 : MP <= 2 ? 2 : MP <= 4 ? 4 : 8; }
+__host__ __device__ constexpr int tapStride(int MP) { return MP <= 1 ? 1 : MP <= 2 ? 2 : MP <= 4 ? 4 : MP <= 8 ? 8 : MP <= 16 ? 16 : 32; }
 
 template <int MP>
 __device__ __forceinline__ void loadTapRow(const float* hT, unsigned p, float (&h)[MP]) {
@@ -156,6 +156,13 @@ __device__ __forceinline__ void loadTapRow(const float* hT, unsigned p, float (&
   }
 }
 
+// Distance between two rows of the staged tile.  A thread reads ITS row 16 bytes at a time, so rows whose length is a multiple of
+// 64 bytes would put a quarter-warp on 2 to 8 of the 8 bank groups; those tiles are staged row by row (one bulk copy per row, issued
+// by the thread that owns it) with 16 bytes of padding, which makes the stride odd in 16-byte units.
+__host__ __device__ constexpr unsigned rowsRowStride(unsigned D, unsigned elemBytes) {
+  return D * elemBytes + ((D * elemBytes >= 128u && (D * elemBytes) % 64u == 0u) ? 16u : 0u);
+}
+
 // Shared-memory carve-up (bytes), identical on host and device.
 struct RowsSmem {
   unsigned mixOff, rotOff, tapOff, tileOff, total;
@@ -172,7 +179,7 @@ __host__ __device__ inline RowsSmem rowsSmemLayout(unsigned D, unsigned TS, unsi
   off += D * TS * 4;
   off = (off + 127u) & ~127u;
   s.tileOff = off;
-  const unsigned tileBytes = rowsPerTile * D * elemBytes;
+  const unsigned tileBytes = rowsPerTile * rowsRowStride(D, elemBytes);
   const unsigned exchBytes = (M > 0 ? (M - 1) : 0) * rowsPerTile * 8 + (fm ? rowsPerTile * 8 : 0);
   off += tileBytes > exchBytes ? tileBytes : exchBytes;
   s.total = off;
@@ -198,21 +205,36 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
   const unsigned tid = threadIdx.x;
   const unsigned long long row0 = static_cast<unsigned long long>(blockIdx.x) * prm.outPerTile;
 
-  // ---- stage the raw tile with one TMA bulk copy ---------------------------------------------------
+  // ---- stage the raw tile: one TMA bulk copy, or one per row when the rows are padded -----------------------------
   const unsigned long long tileStart = row0 * D * ES;
   const unsigned long long totalBytes = prm.nIn * ES;
   const unsigned tileBytes = NT * D * ES;
   const unsigned avail = totalBytes - tileStart < tileBytes ? static_cast<unsigned>(totalBytes - tileStart) : tileBytes;
   const unsigned bulk = avail & ~15u;
+  const unsigned rowBytes = D * ES, rowStride = rowsRowStride(D, ES);
+  const unsigned char* gTile = static_cast<const unsigned char*>(prm.in) + tileStart;
   if (tid == 0) {
     mbarInit(bar, 1);
     fenceMbarInit();
-    mbarExpectTx(bar, bulk);
-    if (bulk) tmaBulkLoad(tile, static_cast<const unsigned char*>(prm.in) + tileStart, bulk, bar);
   }
-  // tail of the last tile: copy the <16 B remainder and zero what lies past the valid input
-  for (unsigned b = bulk + tid; b < tileBytes; b += kRowsThreads) {
-    tile[b] = b < avail ? static_cast<const unsigned char*>(prm.in)[tileStart + b] : 0;
+  if (rowStride == rowBytes) {
+    if (tid == 0) {
+      mbarExpectTx(bar, bulk);
+      if (bulk) tmaBulkLoad(tile, gTile, bulk, bar);
+    }
+    // tail of the last tile: copy the <16 B remainder and zero what lies past the valid input
+    for (unsigned b = bulk + tid; b < tileBytes; b += kRowsThreads) tile[b] = b < avail ? gTile[b] : 0;
+  } else {
+    __syncthreads();  // the barrier is initialised before any thread's copy names it
+    if (tid == 0) mbarExpectTx(bar, bulk);  // rowBytes is a multiple of 16: the rows' bulk parts add up to `bulk`
+#pragma unroll
+    for (int i = 0; i < RPT; i++) {
+      const unsigned row = tid + i * kRowsThreads, start = row * rowBytes;
+      const unsigned have = avail > start ? (avail - start < rowBytes ? avail - start : rowBytes) : 0u;
+      const unsigned rb = have & ~15u;
+      if (rb) tmaBulkLoad(tile + row * rowStride, gTile + start, rb, bar);
+      for (unsigned b = rb; b < rowBytes; b++) tile[row * rowStride + b] = b < have ? gTile[start + b] : 0;
+    }
   }
 
   // ---- tables ----------------------------------------------------------------------------------------
@@ -253,10 +275,9 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
 #pragma unroll
     for (int m = 0; m < MP; m++) acc[i][m] = make_float2(0.0f, 0.0f);
 
-  const unsigned rowBytes = D * ES;
   const unsigned char* rowPtr[RPT];
 #pragma unroll
-  for (int i = 0; i < RPT; i++) rowPtr[i] = tile + (tid + i * kRowsThreads) * rowBytes;
+  for (int i = 0; i < RPT; i++) rowPtr[i] = tile + (tid + i * kRowsThreads) * rowStride;
 
   for (unsigned p = 0; p < D; p += VEC) {
     uint4 v[RPT];

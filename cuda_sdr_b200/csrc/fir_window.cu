@@ -30,11 +30,23 @@ template <typename T>
 struct WinTraits;
 template <>
 struct WinTraits<float2> {
+  using Vec = float4;  // two elements
+  __device__ static void unpack(float4 v, float2 (&x)[2]) {
+    x[0] = make_float2(v.x, v.y);
+    x[1] = make_float2(v.z, v.w);
+  }
   __device__ static float2 zero() { return make_float2(0.0f, 0.0f); }
   __device__ static float2 fma(float h, float2 x, float2 acc) { return __ffma2_rn(make_float2(h, h), x, acc); }
 };
 template <>
 struct WinTraits<float> {
+  using Vec = float4;  // four elements
+  __device__ static void unpack(float4 v, float (&x)[4]) {
+    x[0] = v.x;
+    x[1] = v.y;
+    x[2] = v.z;
+    x[3] = v.w;
+  }
   __device__ static float zero() { return 0.0f; }
   __device__ static float fma(float h, float x, float acc) { return fmaf(h, x, acc); }
 };
@@ -42,15 +54,24 @@ struct WinTraits<float> {
 template <int R>
 __host__ __device__ constexpr unsigned winPadded(unsigned q) { return q + q / R; }  // one pad element per R
 
+// Staged samples keep the order they have in memory: sample (q, pc) -- decimated index q, phase pc of the PC staged -- sits at
+// element q * PC + pc + q / R.  The pad element per R decimated samples makes the stride between the windows of neighbouring
+// threads odd (R * PC + 1), so the R-strided reads of a warp are conflict-free, and for D == PC the whole tile is ONE contiguous
+// run of the input: it is copied with 16-byte loads.
+template <int PC, int R>
+__host__ __device__ constexpr unsigned winSlot(unsigned e) { return e + e / (PC * R); }  // e = q * PC + pc
+
 // PC = phases staged together (divides D); TC = taps per phase staged together (a multiple of R, prm.winTapChunk).
-// Shared memory: taps [PC][TC] floats, then x [PC][winPadded(BO + TC) + 1] elements.
+// Shared memory: taps [PC][kWinMaxTapChunk] floats, then the staged samples.
 template <typename Elem, int PC, int kWinR>
 __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm) {
   extern __shared__ __align__(16) unsigned char wsmem[];
   constexpr unsigned BO = kWinThreads * kWinR;      // outputs per CTA
+  constexpr unsigned VEC = 16 / sizeof(Elem);       // elements per 16-byte load
+  using Vec = typename WinTraits<Elem>::Vec;
   const unsigned TC = prm.winTapChunk;
   const unsigned ROWS = BO + TC;                    // decimated samples staged per phase (window of the tap chunk)
-  const unsigned ROWS_P = (winPadded<kWinR>(ROWS) + 1) | 1u;  // odd: the PC rows of one staged sample fall into different banks
+  const unsigned total = ROWS * PC;                 // elements staged per pass
   float* sTaps = reinterpret_cast<float*>(wsmem);
   Elem* sX = reinterpret_cast<Elem*>(wsmem + PC * kWinMaxTapChunk * sizeof(float));
 
@@ -58,6 +79,9 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
   const unsigned D = prm.D, T = prm.T, M = prm.M;
   const unsigned long long k0 = static_cast<unsigned long long>(blockIdx.x) * BO;  // first output of the CTA
   const Elem* gIn = static_cast<const Elem*>(prm.in) + blockIdx.y * prm.inBatchStride;  // blockIdx.y: independent streams (batched)
+  const bool contiguous = D == PC;
+  // strided tiles: every decimated sample contributes a run of PC elements; whole 16-byte pieces when everything is aligned
+  const bool stridedVec = !contiguous && PC % VEC == 0 && D % VEC == 0 && reinterpret_cast<uintptr_t>(gIn) % 16 == 0;
 
   Elem acc[kWinR];
 #pragma unroll
@@ -72,25 +96,64 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
         const unsigned long long j = static_cast<unsigned long long>(m0 + mm) * D + p0 + pc;
         sTaps[i] = (m0 + mm < M && j < T) ? prm.taps[j] : 0.0f;
       }
-      // samples: sX[pc][pad(q)] = x[(k0 + m0 + q)*D + p0 + pc],  q < ROWS
-      for (unsigned i = tid; i < ROWS * PC; i += kWinThreads) {
-        const unsigned q = i / PC, pc = i % PC;
-        const unsigned long long idx = (k0 + m0 + q) * D + p0 + pc;
-        sX[pc * ROWS_P + winPadded<kWinR>(q)] = idx < prm.nIn ? gIn[idx] : WinTraits<Elem>::zero();
+      // samples: element e = q * PC + pc of the tile is x[(k0 + m0 + q) * D + p0 + pc]
+      const unsigned long long base = (k0 + m0) * D + p0;  // input index of element 0
+      if (contiguous) {
+        const unsigned long long left = base < prm.nIn ? prm.nIn - base : 0;
+        const unsigned valid = left < total ? static_cast<unsigned>(left) : total;  // elements past it are zero
+        const Elem* src = gIn + base;
+        const unsigned head = (VEC - static_cast<unsigned>(reinterpret_cast<uintptr_t>(src) / sizeof(Elem)) % VEC) % VEC;
+        const unsigned nvec = total > head ? (total - head) / VEC : 0;
+        for (unsigned e = tid; e < head && e < total; e += kWinThreads) sX[winSlot<PC, kWinR>(e)] = e < valid ? src[e] : WinTraits<Elem>::zero();
+#pragma unroll 4
+        for (unsigned v = tid; v < nvec; v += kWinThreads) {
+          const unsigned e = head + v * VEC;
+          Elem x[VEC];
+          if (e + VEC <= valid) {
+            WinTraits<Elem>::unpack(*reinterpret_cast<const Vec*>(src + e), x);
+          } else {
+#pragma unroll
+            for (unsigned i = 0; i < VEC; i++) x[i] = e + i < valid ? src[e + i] : WinTraits<Elem>::zero();
+          }
+#pragma unroll
+          for (unsigned i = 0; i < VEC; i++) sX[winSlot<PC, kWinR>(e + i)] = x[i];
+        }
+        for (unsigned e = head + nvec * VEC + tid; e < total; e += kWinThreads) sX[winSlot<PC, kWinR>(e)] = e < valid ? src[e] : WinTraits<Elem>::zero();
+      } else if (stridedVec) {
+#pragma unroll 4
+        for (unsigned v = tid; v < total / VEC; v += kWinThreads) {
+          const unsigned e = v * VEC, q = e / PC, pc = e % PC;
+          const unsigned long long idx = base + static_cast<unsigned long long>(q) * D + pc;
+          Elem x[VEC];
+          if (idx + VEC <= prm.nIn) {
+            WinTraits<Elem>::unpack(*reinterpret_cast<const Vec*>(gIn + idx), x);
+          } else {
+#pragma unroll
+            for (unsigned i = 0; i < VEC; i++) x[i] = idx + i < prm.nIn ? gIn[idx + i] : WinTraits<Elem>::zero();
+          }
+#pragma unroll
+          for (unsigned i = 0; i < VEC; i++) sX[winSlot<PC, kWinR>(e + i)] = x[i];
+        }
+      } else {
+        for (unsigned e = tid; e < total; e += kWinThreads) {
+          const unsigned q = e / PC, pc = e % PC;
+          const unsigned long long idx = base + static_cast<unsigned long long>(q) * D + pc;
+          sX[winSlot<PC, kWinR>(e)] = idx < prm.nIn ? gIn[idx] : WinTraits<Elem>::zero();
+        }
       }
       __syncthreads();
 
 #pragma unroll
       for (int pc = 0; pc < PC; pc++) {
         const float* hs = sTaps + pc * TC;
-        // this thread's window starts at sample base = 8 tid of the staged row; with one pad element per 8 samples, sample
-        // base + 8 a + b (b < 8) sits at 9 tid + 9 a + b: every offset below is a compile-time constant off `xw`
-        const Elem* xw = sX + pc * ROWS_P + tid * (kWinR + 1);
+        // this thread's window starts at decimated sample R * tid of the tile: element tid * (R * PC + 1) + pc; sample j of the
+        // window (j = R a + b) sits (R a + b) * PC + a elements further -- compile-time constants off `xw` inside a block of R taps
+        const Elem* xw = sX + tid * (kWinR * PC + 1) + pc;
         Elem w[kWinR];
 #pragma unroll
-        for (int r = 0; r < kWinR - 1; r++) w[r] = xw[r];
+        for (int r = 0; r < kWinR - 1; r++) w[r] = xw[r * PC];
 #pragma unroll 2
-        for (unsigned mm = 0; mm < TC; mm += kWinR, xw += kWinR + 1) {
+        for (unsigned mm = 0; mm < TC; mm += kWinR, xw += kWinR * PC + 1) {
           // eight taps at a time (TC is a multiple of 8); before tap tau the window holds samples base + tau .. + R - 1, sample
           // base + tau + i in slot (tau + i) % R -- all slot numbers below are compile-time constants
 #pragma unroll
@@ -102,7 +165,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
               for (int u = 0; u < 8; u++) {
                 constexpr int kLast = kWinR - 1;
                 const int c = blk + u + kLast;  // newest sample of the window, relative to the R-aligned block start
-                w[c % kWinR] = xw[c + c / kWinR];
+                w[c % kWinR] = xw[c * PC + c / kWinR];
 #pragma unroll
                 for (int r = 0; r < kWinR; r++) acc[r] = WinTraits<Elem>::fma(h[u], w[(blk + u + r) % kWinR], acc[r]);
               }
@@ -138,7 +201,7 @@ cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
   if (tc > static_cast<unsigned>(kWinMaxTapChunk)) tc = kWinMaxTapChunk;
   prm.winTapChunk = tc;
   const unsigned ROWS = BO + tc;
-  const size_t smem = pc * kWinMaxTapChunk * sizeof(float) + static_cast<size_t>(pc) * ((winPadded<kWinR>(ROWS) + 1) | 1u) * sizeof(Elem);
+  const size_t smem = pc * kWinMaxTapChunk * sizeof(float) + static_cast<size_t>(ROWS * pc + ROWS / kWinR + 1) * sizeof(Elem);
   const unsigned long long blocks = (prm.nOut + BO - 1) / BO;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   void (*k)(const FirParams) = pc == 5 ? windowKernel<Elem, 5, kWinR> : pc == 4 ? windowKernel<Elem, 4, kWinR> : pc == 2 ? windowKernel<Elem, 2, kWinR>

@@ -117,6 +117,44 @@ def test_fir_fc_vs_oracle(ops, T, D, n):
     assert_close(got, ref, what=f"firFC T={T} D={D}")
 
 
+# the corners and the diagonal of bench.py --workload firsweep (T in 32..4096, D in 1..64), every kernel the
+# dispatcher picks for them (rows, staged direct, window with 5 / 4 / 2 / 1 phases per pass and one or several tap chunks)
+SWEEP_SHAPES = [(4096, 64, 1 << 20), (4096, 1, 30000), (1024, 64, 1 << 20), (32, 64, 1 << 19), (32, 1, 20000), (512, 32, 1 << 19),
+                (256, 16, 1 << 18), (128, 8, 1 << 17), (64, 4, 1 << 16), (2048, 2, 40000), (4096, 16, 1 << 19), (1024, 5, 1 << 17)]
+
+
+@pytest.mark.parametrize("T,D,n", SWEEP_SHAPES)
+def test_fir_fc_sweep_cells_vs_oracle(ops, T, D, n):
+    rng = np.random.default_rng(T * 131 + D)
+    taps = (rng.standard_normal(T) / np.sqrt(T)).astype(np.float32)
+    x = _cplx(rng, n + 37)  # ragged length
+    got = ops.fir("fc", torch.from_numpy(taps).to(DEV), torch.from_numpy(x).to(DEV), D).cpu().numpy()
+    ref = orc.fir("fc", taps, x, D)
+    assert got.size == ref.size == orc.fir_num_outputs(x.size, T, D)
+    assert_close(got, ref, what=f"firFC sweep cell T={T} D={D}")
+
+
+@pytest.mark.parametrize("T,D", [(4096, 64), (1024, 64), (4096, 1), (32, 64)])
+def test_fir_fc_sweep_cells_at_bench_size(ops, T, D):
+    """The sweep's own size (2^26 complex samples): exact output count, and windows of outputs (first, last, across CTA borders,
+    random) against the oracle run on exactly the input samples those outputs read (Fir.cpp:262-266)."""
+    n = 1 << 26
+    g = torch.Generator(device=DEV).manual_seed(T + D)
+    xd = torch.view_as_complex(torch.randn(n, 2, device=DEV, dtype=torch.float32, generator=g))
+    rng = np.random.default_rng(T + D)
+    taps = (rng.standard_normal(T) / np.sqrt(T)).astype(np.float32)
+    got = ops.fir("fc", torch.from_numpy(taps).to(DEV), xd, D)
+    n_out = orc.fir_num_outputs(n, T, D)
+    assert got.numel() == n_out
+    W = 96
+    starts = [0, n_out - W, 1024 - 40, 1024 * 147 - 50] + [int(v) for v in rng.integers(0, n_out - W, size=6)]
+    for k0 in starts:
+        xs = xd[k0 * D: (k0 + W) * D + T].cpu().numpy()  # the slice keeps the count rule of the whole input (Fir.cpp:181-186)
+        ref = orc.fir("fc", taps, xs, D)[:W]
+        assert ref.size == W
+        assert_close(got[k0: k0 + W].cpu().numpy(), ref, what=f"firFC T={T} D={D} at 2^26, outputs {k0}..{k0 + W}")
+
+
 @pytest.mark.parametrize("kind", ["ff", "cc", "cf"])
 @pytest.mark.parametrize("T,D,n", [(2, 2, 5), (129, 10, 50000), (273, 5, 40000), (31, 1, 1000), (1500, 4, 20000)])
 def test_fir_other_kinds_vs_oracle(ops, kind, T, D, n):
