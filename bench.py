@@ -733,7 +733,7 @@ def measure_channelizer(args, ctx, steps, warmup, log2n, only_rank0_unsharded=Fa
         _, n_audio = ch.counts(n)
         floats = [len(sharding.channels_of_rank(total, world, r)) * n_audio for r in range(world)]
     n_demod = (n_audio - 1) * D2c + T2c
-    scratch = torch.empty(len(mine), n_demod, dtype=torch.float32, device=dev)
+    scratch = torch.empty(len(mine), (n_demod + 3) // 4 * 4, dtype=torch.float32, device=dev)[:, :n_demod]  # rows 16-byte aligned
     slabs = 3
     gather = ctx.make_gather(floats, slabs) if world > 1 else None
     if gather is not None:

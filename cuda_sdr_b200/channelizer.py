@@ -86,7 +86,8 @@ class Channelizer:
         if out is None:
             out = torch.zeros(self.num_channels, max(n_max, 1), dtype=torch.float32, device=x.device)
         if scratch is None:
-            scratch = torch.empty(self.num_channels, max(n_demod, 1), dtype=torch.float32, device=x.device)
+            # rows 16-byte aligned: the audio stage then copies its tiles with 16-byte loads for every channel
+            scratch = torch.empty(self.num_channels, (max(n_demod, 1) + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :max(n_demod, 1)]
         counts = (C.c_size_t * self.num_channels)()
         st = _lib.b200sdr_channelizer_process(self._h, x.data_ptr(), n_in, scratch.data_ptr(), scratch.stride(0), out.data_ptr(), out.stride(0),
                                               counts, torch.cuda.current_stream(x.device).cuda_stream)
@@ -104,7 +105,8 @@ class Channelizer:
         if out is None:
             out = torch.empty(self.num_channels, max(n_audio, 1), dtype=torch.float32, device=x.device)
         if scratch is None:
-            scratch = torch.empty(self.num_channels, max(n_demod, 1), dtype=torch.float32, device=x.device)
+            # rows 16-byte aligned: the audio stage then copies its tiles with 16-byte loads for every channel
+            scratch = torch.empty(self.num_channels, (max(n_demod, 1) + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :max(n_demod, 1)]
         assert out.stride(1) == 1 and scratch.stride(1) == 1
         st = _lib.b200sdr_channelizer_run(self._h, x.data_ptr(), n_in, scratch.data_ptr(), scratch.stride(0), out.data_ptr(), out.stride(0),
                                           n_audio, torch.cuda.current_stream(x.device).cuda_stream)

@@ -41,6 +41,7 @@ struct FirParams {
   // direct kernel only: blockIdx.y selects one of several independent streams (batched audio FIR of the channelizer)
   unsigned long long inBatchStride, outBatchStride;  // in input / output elements
   unsigned winTapChunk;  // window kernel only: taps per phase staged together (multiple of 8; set by the launcher)
+  unsigned winStreams;   // window kernel only: number of batched streams (set by the launcher)
 };
 
 #ifdef __CUDACC__

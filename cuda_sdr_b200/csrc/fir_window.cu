@@ -10,6 +10,8 @@
 // sample of the CTA's window is read from HBM once.
 #include <gsdr/gsdr.h>
 
+#include <cstdlib>
+
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
 
@@ -51,6 +53,39 @@ struct WinTraits<float> {
   __device__ static float fma(float h, float x, float acc) { return fmaf(h, x, acc); }
 };
 
+// Where a CTA's samples come from.  Plain: one stream of Elem.  Pair: TWO real streams (two channels of the channelizer's audio
+// stage, `stride` floats apart) travel through the kernel as the two halves of a float2, so the real-data FIR runs on packed FFMA2
+// like the complex one: with scalar FFMA every load and address instruction takes an issue slot from the FMA pipe, with FFMA2 the
+// pipe is busy two cycles per issue and the rest fits in between.
+template <typename Elem, bool PAIR>
+struct WinSource {
+  static constexpr unsigned VEC = 16 / sizeof(Elem);
+  const Elem* p;
+  __device__ WinSource(const FirParams& prm, unsigned y) : p(static_cast<const Elem*>(prm.in) + y * prm.inBatchStride) {}
+  __device__ Elem load(unsigned long long i) const { return p[i]; }
+  __device__ void loadVec(unsigned long long i, Elem (&x)[VEC]) const { WinTraits<Elem>::unpack(*reinterpret_cast<const float4*>(p + i), x); }
+  __device__ unsigned misalign(unsigned long long i) const { return static_cast<unsigned>(reinterpret_cast<uintptr_t>(p + i) / sizeof(Elem)) % VEC; }
+  __device__ bool vecOk() const { return true; }
+};
+template <>
+struct WinSource<float2, true> {
+  static constexpr unsigned VEC = 4;
+  const float *a, *b;  // b == nullptr: an odd number of streams, the last one travels alone
+  __device__ WinSource(const FirParams& prm, unsigned y)
+      : a(static_cast<const float*>(prm.in) + 2ull * y * prm.inBatchStride), b(2 * y + 1 < prm.winStreams ? a + prm.inBatchStride : nullptr) {}
+  __device__ float2 load(unsigned long long i) const { return make_float2(a[i], b ? b[i] : 0.0f); }
+  __device__ void loadVec(unsigned long long i, float2 (&x)[4]) const {
+    const float4 u = *reinterpret_cast<const float4*>(a + i);
+    const float4 v = b ? *reinterpret_cast<const float4*>(b + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    x[0] = make_float2(u.x, v.x);
+    x[1] = make_float2(u.y, v.y);
+    x[2] = make_float2(u.z, v.z);
+    x[3] = make_float2(u.w, v.w);
+  }
+  __device__ unsigned misalign(unsigned long long i) const { return static_cast<unsigned>(reinterpret_cast<uintptr_t>(a + i) / sizeof(float)) % 4u; }
+  __device__ bool vecOk() const { return b == nullptr || (reinterpret_cast<uintptr_t>(a) - reinterpret_cast<uintptr_t>(b)) % 16 == 0; }
+};
+
 template <int R>
 __host__ __device__ constexpr unsigned winPadded(unsigned q) { return q + q / R; }  // one pad element per R
 
@@ -63,12 +98,12 @@ __host__ __device__ constexpr unsigned winSlot(unsigned e) { return e + e / (PC 
 
 // PC = phases staged together (divides D); TC = taps per phase staged together (a multiple of R, prm.winTapChunk).
 // Shared memory: taps [PC][kWinMaxTapChunk] floats, then the staged samples.
-template <typename Elem, int PC, int kWinR>
+template <typename Elem, int PC, int kWinR, bool PAIR>
 __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm) {
   extern __shared__ __align__(16) unsigned char wsmem[];
+  using Source = WinSource<Elem, PAIR>;
   constexpr unsigned BO = kWinThreads * kWinR;      // outputs per CTA
-  constexpr unsigned VEC = 16 / sizeof(Elem);       // elements per 16-byte load
-  using Vec = typename WinTraits<Elem>::Vec;
+  constexpr unsigned VEC = Source::VEC;             // elements per vector load (16 bytes of every stream)
   const unsigned TC = prm.winTapChunk;
   const unsigned ROWS = BO + TC;                    // decimated samples staged per phase (window of the tap chunk)
   const unsigned total = ROWS * PC;                 // elements staged per pass
@@ -78,10 +113,10 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
   const unsigned tid = threadIdx.x;
   const unsigned D = prm.D, T = prm.T, M = prm.M;
   const unsigned long long k0 = static_cast<unsigned long long>(blockIdx.x) * BO;  // first output of the CTA
-  const Elem* gIn = static_cast<const Elem*>(prm.in) + blockIdx.y * prm.inBatchStride;  // blockIdx.y: independent streams (batched)
+  const Source src(prm, blockIdx.y);  // blockIdx.y: independent streams (batched), or pairs of them
   const bool contiguous = D == PC;
   // strided tiles: every decimated sample contributes a run of PC elements; whole 16-byte pieces when everything is aligned
-  const bool stridedVec = !contiguous && PC % VEC == 0 && D % VEC == 0 && reinterpret_cast<uintptr_t>(gIn) % 16 == 0;
+  const bool stridedVec = !contiguous && PC % VEC == 0 && D % VEC == 0 && src.vecOk() && src.misalign(0) == 0;
 
   Elem acc[kWinR];
 #pragma unroll
@@ -101,24 +136,28 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
       if (contiguous) {
         const unsigned long long left = base < prm.nIn ? prm.nIn - base : 0;
         const unsigned valid = left < total ? static_cast<unsigned>(left) : total;  // elements past it are zero
-        const Elem* src = gIn + base;
-        const unsigned head = (VEC - static_cast<unsigned>(reinterpret_cast<uintptr_t>(src) / sizeof(Elem)) % VEC) % VEC;
-        const unsigned nvec = total > head ? (total - head) / VEC : 0;
-        for (unsigned e = tid; e < head && e < total; e += kWinThreads) sX[winSlot<PC, kWinR>(e)] = e < valid ? src[e] : WinTraits<Elem>::zero();
+        unsigned head = total, nvec = 0;  // [0, head) one by one, nvec vectors, the rest one by one
+        if (src.vecOk()) {
+          head = (VEC - src.misalign(base)) % VEC;
+          if (head > total) head = total;
+          nvec = (total - head) / VEC;
+        }
+        for (unsigned e = tid; e < head; e += kWinThreads) sX[winSlot<PC, kWinR>(e)] = e < valid ? src.load(base + e) : WinTraits<Elem>::zero();
 #pragma unroll 4
         for (unsigned v = tid; v < nvec; v += kWinThreads) {
           const unsigned e = head + v * VEC;
           Elem x[VEC];
           if (e + VEC <= valid) {
-            WinTraits<Elem>::unpack(*reinterpret_cast<const Vec*>(src + e), x);
+            src.loadVec(base + e, x);
           } else {
 #pragma unroll
-            for (unsigned i = 0; i < VEC; i++) x[i] = e + i < valid ? src[e + i] : WinTraits<Elem>::zero();
+            for (unsigned i = 0; i < VEC; i++) x[i] = e + i < valid ? src.load(base + e + i) : WinTraits<Elem>::zero();
           }
 #pragma unroll
           for (unsigned i = 0; i < VEC; i++) sX[winSlot<PC, kWinR>(e + i)] = x[i];
         }
-        for (unsigned e = head + nvec * VEC + tid; e < total; e += kWinThreads) sX[winSlot<PC, kWinR>(e)] = e < valid ? src[e] : WinTraits<Elem>::zero();
+        for (unsigned e = head + nvec * VEC + tid; e < total; e += kWinThreads)
+          sX[winSlot<PC, kWinR>(e)] = e < valid ? src.load(base + e) : WinTraits<Elem>::zero();
       } else if (stridedVec) {
 #pragma unroll 4
         for (unsigned v = tid; v < total / VEC; v += kWinThreads) {
@@ -126,10 +165,10 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
           const unsigned long long idx = base + static_cast<unsigned long long>(q) * D + pc;
           Elem x[VEC];
           if (idx + VEC <= prm.nIn) {
-            WinTraits<Elem>::unpack(*reinterpret_cast<const Vec*>(gIn + idx), x);
+            src.loadVec(idx, x);
           } else {
 #pragma unroll
-            for (unsigned i = 0; i < VEC; i++) x[i] = idx + i < prm.nIn ? gIn[idx + i] : WinTraits<Elem>::zero();
+            for (unsigned i = 0; i < VEC; i++) x[i] = idx + i < prm.nIn ? src.load(idx + i) : WinTraits<Elem>::zero();
           }
 #pragma unroll
           for (unsigned i = 0; i < VEC; i++) sX[winSlot<PC, kWinR>(e + i)] = x[i];
@@ -138,7 +177,7 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
         for (unsigned e = tid; e < total; e += kWinThreads) {
           const unsigned q = e / PC, pc = e % PC;
           const unsigned long long idx = base + static_cast<unsigned long long>(q) * D + pc;
-          sX[winSlot<PC, kWinR>(e)] = idx < prm.nIn ? gIn[idx] : WinTraits<Elem>::zero();
+          sX[winSlot<PC, kWinR>(e)] = idx < prm.nIn ? src.load(idx) : WinTraits<Elem>::zero();
         }
       }
       __syncthreads();
@@ -184,16 +223,31 @@ __global__ void __launch_bounds__(kWinThreads) windowKernel(const FirParams prm)
 #pragma unroll
   for (int r = 0; r < kWinR; r++) sOut[tid * (kWinR + 1) + r] = acc[r];
   __syncthreads();
-  Elem* out = static_cast<Elem*>(prm.out) + blockIdx.y * prm.outBatchStride;
+  if constexpr (PAIR) {
+    float* outA = static_cast<float*>(prm.out) + 2ull * blockIdx.y * prm.outBatchStride;
+    float* outB = 2 * blockIdx.y + 1 < prm.winStreams ? outA + prm.outBatchStride : nullptr;
 #pragma unroll
-  for (int j = 0; j < kWinR; j++) {
-    const unsigned o = j * kWinThreads + tid;
-    const unsigned long long k = k0 + o;
-    if (k < prm.nOut) out[k] = sOut[winPadded<kWinR>(o)];
+    for (int j = 0; j < kWinR; j++) {
+      const unsigned o = j * kWinThreads + tid;
+      const unsigned long long k = k0 + o;
+      if (k < prm.nOut) {
+        const float2 y = sOut[winPadded<kWinR>(o)];
+        outA[k] = y.x;
+        if (outB) outB[k] = y.y;
+      }
+    }
+  } else {
+    Elem* out = static_cast<Elem*>(prm.out) + blockIdx.y * prm.outBatchStride;
+#pragma unroll
+    for (int j = 0; j < kWinR; j++) {
+      const unsigned o = j * kWinThreads + tid;
+      const unsigned long long k = k0 + o;
+      if (k < prm.nOut) out[k] = sOut[winPadded<kWinR>(o)];
+    }
   }
 }
 
-template <typename Elem, int kWinR>
+template <typename Elem, int kWinR, bool PAIR>
 cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
   const unsigned pc = prm.D % 5 == 0 ? 5u : prm.D % 4 == 0 ? 4u : prm.D % 2 == 0 ? 2u : 1u;
   constexpr unsigned BO = kWinThreads * kWinR;
@@ -204,14 +258,17 @@ cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
   const size_t smem = pc * kWinMaxTapChunk * sizeof(float) + static_cast<size_t>(ROWS * pc + ROWS / kWinR + 1) * sizeof(Elem);
   const unsigned long long blocks = (prm.nOut + BO - 1) / BO;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-  void (*k)(const FirParams) = pc == 5 ? windowKernel<Elem, 5, kWinR> : pc == 4 ? windowKernel<Elem, 4, kWinR> : pc == 2 ? windowKernel<Elem, 2, kWinR>
-                                                                                                                  : windowKernel<Elem, 1, kWinR>;
+  void (*k)(const FirParams) = pc == 5   ? windowKernel<Elem, 5, kWinR, PAIR>
+                               : pc == 4 ? windowKernel<Elem, 4, kWinR, PAIR>
+                               : pc == 2 ? windowKernel<Elem, 2, kWinR, PAIR>
+                                         : windowKernel<Elem, 1, kWinR, PAIR>;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
   }
   if (batch == 0 || batch > 65535u) return cudaErrorInvalidConfiguration;
-  k<<<dim3(static_cast<unsigned>(blocks), batch), kWinThreads, smem, stream>>>(prm);
+  prm.winStreams = batch;
+  k<<<dim3(static_cast<unsigned>(blocks), PAIR ? (batch + 1) / 2 : batch), kWinThreads, smem, stream>>>(prm);
   return launchStatus();
 }
 
@@ -229,7 +286,11 @@ cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream) { return 
 cudaError_t launchWindowBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream) {
   prm.M = (prm.T + prm.D - 1) / prm.D;
   if (batch == 1) prm.inBatchStride = prm.outBatchStride = 0;
-  return elem == kElemComplex ? launchWindowT<float2, kWinR>(prm, batch, stream) : launchWindowT<float, kWinR>(prm, batch, stream);
+  if (elem == kElemComplex) return launchWindowT<float2, kWinR, false>(prm, batch, stream);
+  // real data: two streams at a time as the halves of a float2 (see WinSource); a single stream keeps the scalar kernel
+  static const bool noPair = std::getenv("B200SDR_WINDOW_NO_PAIR") != nullptr;
+  if (batch >= 2 && !noPair) return launchWindowT<float2, kWinR, true>(prm, batch, stream);
+  return launchWindowT<float, kWinR, false>(prm, batch, stream);
 }
 
 }  // namespace b200sdr
