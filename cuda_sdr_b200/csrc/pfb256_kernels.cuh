@@ -23,6 +23,8 @@
 // split over CTAs, launches or GPUs (time segments concatenate bit-exactly).
 #pragma once
 
+#include <type_traits>
+
 #include "pfb_kernels.cuh"
 
 namespace b200sdr {
@@ -244,6 +246,10 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
     hi[q] = have ? *reinterpret_cast<const double2*>(prm.tapsIm + q * 256 + r) : make_double2(0.0, 0.0);
   }
   const double2 acc0a = prm.acc0[r], acc0b = prm.acc0[r + 1u];
+  // The last tap of a phase exists only for the first T - 256 (QN - 1) phases (T = 4097: phase 0 alone); a warp whose 64 phases all
+  // have a zero there skips that step of the filter bank -- adding 0 * x changes nothing, so the result is the same bit for bit.
+  const bool lastTapLive =
+      __any_sync(0xffffffffu, hr[QN - 1].x != 0.0 || hr[QN - 1].y != 0.0 || hi[QN - 1].x != 0.0 || hi[QN - 1].y != 0.0) != 0;
   __syncthreads();
 
   // (thread 0) chunk c = stream bytes [c CH, (c + 1) CH) relative to s0Bytes -> ring, clipped to the input
@@ -293,19 +299,39 @@ __global__ void __launch_bounds__(kP2Threads, 2) pfb256Kernel(const Pfb256Params
       ua[o] = acc0a;
       ub[o] = acc0b;
     }
-    const unsigned roundBase = j * CH + 2u * r;
+    const unsigned roundBase = (j * CH + 2u * r) & (kP2Ring - 1u);
+    // The round's window (four outputs 2 D bytes apart, QN taps 512 bytes apart) wraps around the ring's end in about a third of
+    // the rounds; in the others every load is base-of-output + constant, with no address arithmetic per sample.
+    const bool wraps = roundBase + 6u * D + static_cast<unsigned>(QN - 1) * 512u + 4u > kP2Ring;
+    const unsigned char* outBase[4];
 #pragma unroll
-    for (int q = 0; q < QN; q++) {
+    for (int o = 0; o < 4; o++) outBase[o] = ring + roundBase + static_cast<unsigned>(o) * 2u * D;
+    auto tapStep = [&](int q, auto wrapTag) {
 #pragma unroll
       for (int o = 0; o < 4; o++) {
-        const unsigned off = (roundBase + static_cast<unsigned>(o) * 2u * D + static_cast<unsigned>(q) * 512u) & (kP2Ring - 1u);
-        const unsigned w = *reinterpret_cast<const unsigned*>(ring + off) ^ 0x80808080u;  // I0 Q0 I1 Q1, biased to unsigned
+        unsigned w;
+        if constexpr (decltype(wrapTag)::value) {
+          const unsigned off = (roundBase + static_cast<unsigned>(o) * 2u * D + static_cast<unsigned>(q) * 512u) & (kP2Ring - 1u);
+          w = *reinterpret_cast<const unsigned*>(ring + off);
+        } else {
+          w = *reinterpret_cast<const unsigned*>(outBase[o] + q * 512);
+        }
+        w ^= 0x80808080u;  // I0 Q0 I1 Q1, biased to unsigned
         const double i0 = pfbSample<0x7650>(w), q0 = pfbSample<0x7651>(w), i1 = pfbSample<0x7652>(w), q1 = pfbSample<0x7653>(w);
         ua[o].x = fma(hr[q].x, i0, fma(-hi[q].x, q0, ua[o].x));
         ua[o].y = fma(hr[q].x, q0, fma(hi[q].x, i0, ua[o].y));
         ub[o].x = fma(hr[q].y, i1, fma(-hi[q].y, q1, ub[o].x));
         ub[o].y = fma(hr[q].y, q1, fma(hi[q].y, i1, ub[o].y));
       }
+    };
+    if (wraps) {
+#pragma unroll
+      for (int q = 0; q < QN - 1; q++) tapStep(q, std::true_type());
+      if (lastTapLive) tapStep(QN - 1, std::true_type());
+    } else {
+#pragma unroll
+      for (int q = 0; q < QN - 1; q++) tapStep(q, std::false_type());
+      if (lastTapLive) tapStep(QN - 1, std::false_type());
     }
 #pragma unroll
     for (int o = 0; o < 4; o++) {
