@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(kRowsThreads) rowsKernel(const FirParams prm) 
 #pragma unroll
   for (int i = 0; i < RPT; i++) rowPtr[i] = tile + (tid + i * kRowsThreads) * rowStride;
 
+  // wide variants: two iterations in flight, so that the next sample pair's tap rows (MP / 2 LDS.128) load under this pair's FMAs
+#pragma unroll(MP >= 16 ? 2 : 1)
   for (unsigned p = 0; p < D; p += VEC) {
     uint4 v[RPT];
 #pragma unroll

@@ -6,18 +6,25 @@
 //
 // This is the `e2e` leg of bench.py: the same Sink/Source calls an application written against the reference makes
 // (src/applications/nbfm_test.cpp:256-354), with the five-node chain replaced by the fused node.  The producer stands in
-// for HackrfSource: it writes synthetic int8 IQ STRAIGHT into the copy node's pinned block (requestBuffer -> write ->
-// commitBuffer), so the only host copy on the path is the producer's own write.
+// for a capture source (HackrfSource / FileSource reading a recording from the page cache): a pool of host threads copies the
+// next block of a pre-generated synthetic int8 IQ capture STRAIGHT into the copy node's pinned block (requestBuffer -> write
+// -> commitBuffer), so the only host copy on the path is the producer's own write.
 //
 // usage: filter_api_bench --taps1 F32 --taps2 F32 [--fs HZ --freq HZ --mod am|fm --dev HZ --d1 N --d2 N] [--device I]
-//          [--samples-per-pass N --passes P --step BYTES --warmup-steps W --pipeline 0|1 --threads T]
+//          [--samples-per-pass N --passes P --step BYTES --warmup-steps W --pipeline 0|1 --threads T --producer copy|resident]
+// --producer resident models a capture device that DMAs into the pinned block itself: a block is written the first time the
+// copy node hands it out and committed as it is afterwards (no host copy in the timed region; the H2D copy stays).
 // Prints one JSON line.
 #include <cuda_runtime.h>
 #include <gpusdrpipeline/EventPipeline.h>
 #include <gpusdrpipeline/Factories.h>
 #include <gpusdrpipeline/FusedChain.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -43,33 +50,86 @@ static vector<float> readFloats(const string& path) {
   return v;
 }
 
-// every producer thread writes its share of the block: xorshift64* bytes = full-range int8 IQ noise
-static void produce(uint8_t* dst, size_t bytes, uint64_t seed, unsigned threads) {
-  auto fill = [=](size_t lo, size_t hi) {
-    uint64_t x = seed ^ (lo * 0x9E3779B97F4A7C15ull) ^ 0x2545F4914F6CDD1Dull;
-    size_t i = lo;
-    for (; i + 8 <= hi; i += 8) {
-      x ^= x >> 12;
-      x ^= x << 25;
-      x ^= x >> 27;
-      const uint64_t v = x * 0x2545F4914F6CDD1Dull;
-      memcpy(dst + i, &v, 8);
-    }
-    for (; i < hi; i++) dst[i] = static_cast<uint8_t>(x >> (8 * (i & 7)));
-  };
-  if (threads <= 1 || bytes <= (size_t(1) << 20)) {
-    fill(0, bytes);
-    return;
+// xorshift64* bytes = full-range int8 IQ noise
+static void fillNoise(uint8_t* dst, size_t lo, size_t hi, uint64_t seed) {
+  uint64_t x = seed ^ (lo * 0x9E3779B97F4A7C15ull) ^ 0x2545F4914F6CDD1Dull;
+  size_t i = lo;
+  for (; i + 8 <= hi; i += 8) {
+    x ^= x >> 12;
+    x ^= x << 25;
+    x ^= x >> 27;
+    const uint64_t v = x * 0x2545F4914F6CDD1Dull;
+    memcpy(dst + i, &v, 8);
   }
-  const size_t per = ((bytes + threads - 1) / threads + 63) & ~size_t(63);
-  vector<thread> pool;
-  for (unsigned t = 0; t < threads; t++) {
-    const size_t lo = t * per, hi = lo + per < bytes ? lo + per : bytes;
-    if (lo >= bytes) break;
-    pool.emplace_back(fill, lo, hi);
-  }
-  for (auto& th : pool) th.join();
+  for (; i < hi; i++) dst[i] = static_cast<uint8_t>(x >> (8 * (i & 7)));
 }
+
+// A fixed pool of producer threads (created once: a block is ~1 ms of work, thread start-up would show).  run(n, fn) calls
+// fn(lo, hi) on the threads' shares of [0, n) and returns when all are done.
+class Pool {
+ public:
+  explicit Pool(unsigned threads) : mCount(threads ? threads : 1) {
+    for (unsigned t = 1; t < mCount; t++) mThreads.emplace_back([this, t] { worker(t); });
+  }
+  ~Pool() {
+    {
+      lock_guard<mutex> lock(mMutex);
+      mStop = true;
+      mGeneration++;
+    }
+    mWake.notify_all();
+    for (auto& th : mThreads) th.join();
+  }
+  void run(size_t n, const function<void(size_t, size_t)>& fn) {
+    if (mCount == 1 || n <= (size_t(1) << 20)) {
+      fn(0, n);
+      return;
+    }
+    {
+      lock_guard<mutex> lock(mMutex);
+      mFn = &fn;
+      mN = n;
+      mPending = mCount - 1;
+      mGeneration++;
+    }
+    mWake.notify_all();
+    share(0);
+    unique_lock<mutex> lock(mMutex);
+    mDone.wait(lock, [this] { return mPending == 0; });
+  }
+
+ private:
+  void share(unsigned t) {
+    const size_t per = ((mN + mCount - 1) / mCount + 63) & ~size_t(63);
+    const size_t lo = t * per, hi = lo + per < mN ? lo + per : mN;
+    if (lo < hi) (*mFn)(lo, hi);
+  }
+  void worker(unsigned t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        unique_lock<mutex> lock(mMutex);
+        mWake.wait(lock, [&] { return mGeneration != seen; });
+        seen = mGeneration;
+        if (mStop) return;
+      }
+      share(t);
+      {
+        lock_guard<mutex> lock(mMutex);
+        if (--mPending == 0) mDone.notify_one();
+      }
+    }
+  }
+  unsigned mCount;
+  vector<thread> mThreads;
+  mutex mMutex;
+  condition_variable mWake, mDone;
+  const function<void(size_t, size_t)>* mFn = nullptr;
+  size_t mN = 0;
+  unsigned mPending = 0;
+  uint64_t mGeneration = 0;
+  bool mStop = false;
+};
 
 int main(int argc, char** argv) {
   double fs = 19.2e6, freq = -1.234e6, dev = 75e3;
@@ -78,6 +138,7 @@ int main(int argc, char** argv) {
   int device = 0;
   bool pipelined = true;
   unsigned threads = 0;
+  bool resident = false;
   for (int i = 1; i + 1 < argc; i += 2) {
     const string k = argv[i], v = argv[i + 1];
     if (k == "--fs") fs = atof(v.c_str());
@@ -95,6 +156,7 @@ int main(int argc, char** argv) {
     else if (k == "--warmup-steps") warmupSteps = strtoull(v.c_str(), nullptr, 10);
     else if (k == "--pipeline") pipelined = v != "0";
     else if (k == "--threads") threads = static_cast<unsigned>(strtoul(v.c_str(), nullptr, 10));
+    else if (k == "--producer") resident = v == "resident";
     else {
       fprintf(stderr, "unknown argument %s\n", k.c_str());
       return 2;
@@ -137,6 +199,11 @@ int main(int argc, char** argv) {
   if (pipelined) pipeline = unwrap(gsCreateEventPipeline(queue));
 
   const size_t passBytes = samplesPerPass * 2;
+  // the "capture": two blocks of noise; every step copies one block's worth from a different offset
+  Pool pool(threads);
+  vector<uint8_t*> filledBlocks;  // --producer resident: pinned blocks that already hold a full block of samples
+  vector<uint8_t> capture(2 * step + 64);
+  pool.run(capture.size(), [&](size_t lo, size_t hi) { fillNoise(capture.data(), lo, hi, 0x9E3779B97F4A7C15ull); });
   size_t total = 0, timedFrom = 0, outputs = 0, stepNo = 0, h2dBytes = 0, d2hBytes = 0;
   double checksum = 0.0;
   int pendingSlot = -1;  // result buffer whose copy was enqueued one step ago and has not been read yet
@@ -169,7 +236,15 @@ int main(int argc, char** argv) {
       size_t bytes = passBytes - pos < step ? passBytes - pos : step;
       bytes &= ~size_t(1);
       Ref<IBuffer> staged = unwrap(h2d->requestBuffer(0, bytes));
-      produce(staged->writePtr(), bytes, 0x9E3779B97F4A7C15ull + stepNo, threads);
+      uint8_t* const block = staged->writePtr();
+      bool written = false;
+      for (uint8_t* seen : filledBlocks) written = written || seen == block;
+      if (!resident || !written) {
+        if (!written && filledBlocks.size() < 16) filledBlocks.push_back(block);
+        uint8_t* dst = block;
+        const uint8_t* src = capture.data() + (stepNo * 4099 * 2) % step;  // whole samples, a different offset every step
+        pool.run(bytes, [=](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+      }
       THROW_IF_ERR(h2d->commitBuffer(0, bytes));
       pos += bytes;
       total += bytes / 2;
@@ -213,6 +288,6 @@ int main(int argc, char** argv) {
   printf("{\"samples\": %zu, \"timed_samples\": %zu, \"timed_steps\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, "
          "\"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"pipeline\": %s, \"threads\": %u, \"device\": %d, \"checksum\": %.6g}\n",
          total, total - timedFrom, timedSteps, outputs, secs, static_cast<double>(total - timedFrom) / secs / 1e6, step, h2dBytes, d2hBytes,
-         pipelined ? "true" : "false", threads, device, checksum);
+         pipelined ? "true" : "false", threads, device, resident ? "resident" : "copy", checksum);
   return 0;
 }
