@@ -566,25 +566,37 @@ def run_chain(args, ctx):
             gather.finish()
         ctx.barrier()
 
-    # warm-up, part 1b (N > 1, balanced): the rate of every GPU UNDER THE LOAD OF THE RUN -- all ranks stepping in lockstep with equal
-    # segments, the gather active (rank 0 absorbing the others' audio) -- from CUDA events around each kernel; the median of
-    # `cal` steps.  A rate measured on each GPU alone misjudges exactly the rank that matters (rank 0).
+    # warm-up, part 1b (N > 1, balanced): the rate of every GPU UNDER THE CONDITIONS OF THE TIMED REGION -- rehearsals of exactly
+    # what is timed below (all ranks start together after a barrier, the same number of steps, the gather active, rank 0
+    # absorbing the others' audio), each rank timing its own kernels with one event pair around the whole run.  The GPUs of a box
+    # differ by a few per cent and power capping moves them further apart under load; a rate measured on each GPU alone, or over
+    # a few kernels, misjudges exactly the ranks that matter.  Two rounds: equal segments first, then a damped correction.
     shares = rates = None
     if balance:
-        cal = 32
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(cal)]
-        quiesce()
-        run_steps(cal, events=evs)
-        quiesce()
-        my_rate = 1.0 / max(statistics.median(a.elapsed_time(b) for a, b in evs), 1e-6)  # steps per millisecond
-        rates = [r if r > 0 else 1.0 for r in ctx.gather_objects(my_rate)]
-        mean = sum(rates) / world
-        weights = [min(max(r / mean, 0.90), 1.10) for r in rates]  # stay inside the allocation whatever a noisy measurement says
         total_audio = chain.counts(world * n)[2]
-        segs = [chain.segment_weighted(total_audio, weights, r) for r in range(world)]
-        set_partition(segs)
+        weights = [1.0] * world
+        cal_a, cal_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rnd in range(2):
+            times = []
+            for _ in range(2):
+                quiesce()
+                cal_a.record()
+                run_steps(args.steps)
+                cal_b.record()
+                quiesce()
+                times.append(cal_a.elapsed_time(cal_b))
+                extra += args.steps
+            mine = min(times)  # ms for this rank's share of args.steps steps
+            all_ms = [t if t > 0 else 1.0 for t in ctx.gather_objects(mine)]
+            mean_ms = sum(all_ms) / world
+            damp = 1.0 if rnd == 0 else 0.7
+            weights = [w * (mean_ms / t) ** damp for w, t in zip(weights, all_ms)]
+            norm = sum(weights) / world
+            weights = [min(max(w / norm, 0.90), 1.10) for w in weights]  # stay inside the allocation whatever a noisy measurement says
+            segs = [chain.segment_weighted(total_audio, weights, r) for r in range(world)]
+            set_partition(segs)
+            rates = [args.steps / t for t in all_ms]  # steps per ms of the last rehearsal round
         shares = [sg[3] / n for sg in segs]
-        extra += cal
     my_in, my_first_in, my_audio = part["in"], part["first"], part["audio"]
     # warm-up, part 2: max(W, 3) complete steps including the gather, in lockstep on every rank
     n_warm = max(args.warmup, 3)
@@ -687,9 +699,9 @@ def run_chain(args, ctx):
                               "steps_per_slab": slab_schedule(args.steps), "slabs": slabs, "calls": gstats["gathers"], "nccl_version": gstats["nccl_version"],
                               "bytes_into_rank0_per_step": 4 * sum(part["counts"][1:])}
         if shares is not None:
-            line["balance"] = {"what": "time segments in proportion to each GPU's rate measured in the warm-up (b200sdr_chain_segment_weighted); "
+            line["balance"] = {"what": "time segments in proportion to each GPU's rate measured in warm-up rehearsals of the timed region (b200sdr_chain_segment_weighted); "
                                        "the step's total stays n_gpus * samples_per_gpu_per_step",
-                               "segment_samples_over_average": shares, "calibration_steps_per_ms": rates}
+                               "segment_samples_over_average": shares, "rehearsal_steps_per_ms": rates}
         if e2e:
             line["e2e"] = e2e
     part.clear()
