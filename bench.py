@@ -439,18 +439,22 @@ def e2e_filter_api(ctx, wl):
             info = json.loads(res.stdout.strip().splitlines()[-1])
         except Exception as e:
             info = {"error": str(e)[:200]}
-        resident = None
-        if ctx.world == 1 and "error" not in info:
-            # the same path with the samples already IN the pinned block (a capture device that DMAs there): what the library and
-            # PCIe allow when the producer costs nothing.  Reported beside the headline, never as it.
-            try:
-                res = subprocess.run(cmd + ["--producer", "resident"], capture_output=True, text=True, timeout=300)
-                resident = json.loads(res.stdout.strip().splitlines()[-1])
-            except Exception:
-                resident = None
+        # the same path with the samples already IN the pinned block (a capture device that DMAs there): what the library and
+        # PCIe allow when the producer costs nothing (at N > 1 the producers of all ranks share the host's cores and memory
+        # bandwidth).  Reported beside the headline, never as it.
+        ctx.barrier()
+        try:
+            res = subprocess.run(cmd + ["--producer", "resident"], capture_output=True, text=True, timeout=300)
+            resident = json.loads(res.stdout.strip().splitlines()[-1])
+        except Exception:
+            resident = None
     infos = ctx.gather_objects(info)
+    residents = ctx.gather_objects(resident)
     if ctx.rank != 0:
         return None
+    resident = None
+    if all(r and "seconds" in r for r in residents):
+        resident = {"msps": sum(r["timed_samples"] for r in residents) / max(r["seconds"] for r in residents) / 1e6}
     if any("error" in i for i in infos):
         return {"value": None, "unit": UNIT, "error": next(i["error"] for i in infos if "error" in i)}
     secs = max(i["seconds"] for i in infos)
