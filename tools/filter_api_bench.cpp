@@ -219,6 +219,10 @@ int main(int argc, char** argv) {
     cudaStreamSynchronize(queue->cudaStream());
   };
   IBuffer* o[1];
+  // host time per phase of the loop (timed region only), printed with the result: where the producer thread waits
+  double tRequest = 0, tProduce = 0, tEnqueue = 0, tWait = 0;
+  auto now = [] { return chrono::steady_clock::now(); };
+  auto since = [&](chrono::steady_clock::time_point t0) { return chrono::duration<double>(now() - t0).count(); };
   auto start = chrono::steady_clock::now();
   for (size_t pass = 0; pass < passes; pass++) {
     for (size_t pos = 0; pos < passBytes; stepNo++) {
@@ -231,11 +235,15 @@ int main(int argc, char** argv) {
         sync();
         timedFrom = total;
         h2dBytes = d2hBytes = 0;
+        tRequest = tProduce = tEnqueue = tWait = 0;
         start = chrono::steady_clock::now();
       }
       size_t bytes = passBytes - pos < step ? passBytes - pos : step;
       bytes &= ~size_t(1);
+      auto t0 = now();
       Ref<IBuffer> staged = unwrap(h2d->requestBuffer(0, bytes));
+      tRequest += since(t0);
+      t0 = now();
       uint8_t* const block = staged->writePtr();
       bool written = false;
       for (uint8_t* seen : filledBlocks) written = written || seen == block;
@@ -245,6 +253,8 @@ int main(int argc, char** argv) {
         const uint8_t* src = capture.data() + (stepNo * 4099 * 2) % step;  // whole samples, a different offset every step
         pool.run(bytes, [=](size_t lo, size_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
       }
+      tProduce += since(t0);
+      t0 = now();
       THROW_IF_ERR(h2d->commitBuffer(0, bytes));
       pos += bytes;
       total += bytes / 2;
@@ -267,6 +277,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "result buffer too small\n");
         return 3;
       }
+      tEnqueue += since(t0);
+      t0 = now();
       if (pipelined) {
         // wait for the PREVIOUS step only (src/filters/Waiter.cpp:34-50): this step's copies and kernel keep running
         THROW_IF_ERR(pipeline->recordNextAndWaitPrevious());
@@ -276,6 +288,7 @@ int main(int argc, char** argv) {
         sync();  // a stream synchronisation per step, as nbfm_test.cpp:346-347 does
         harvest(slot);
       }
+      tWait += since(t0);
     }
   }
   if (pendingSlot >= 0) {
@@ -286,8 +299,10 @@ int main(int argc, char** argv) {
   const double secs = chrono::duration<double>(chrono::steady_clock::now() - start).count();
   const size_t timedSteps = stepNo > warmupSteps ? stepNo - warmupSteps : stepNo;
   printf("{\"samples\": %zu, \"timed_samples\": %zu, \"timed_steps\": %zu, \"outputs\": %zu, \"seconds\": %.6f, \"msps\": %.3f, \"step_bytes\": %zu, "
-         "\"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"pipeline\": %s, \"threads\": %u, \"device\": %d, \"checksum\": %.6g}\n",
+         "\"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"pipeline\": %s, \"threads\": %u, \"device\": %d, \"producer\": \"%s\", "
+         "\"host_ms_per_step\": {\"request\": %.4f, \"produce\": %.4f, \"enqueue\": %.4f, \"wait\": %.4f}, \"checksum\": %.6g}\n",
          total, total - timedFrom, timedSteps, outputs, secs, static_cast<double>(total - timedFrom) / secs / 1e6, step, h2dBytes, d2hBytes,
-         pipelined ? "true" : "false", threads, device, resident ? "resident" : "copy", checksum);
+         pipelined ? "true" : "false", threads, device, resident ? "resident" : "copy", 1e3 * tRequest / timedSteps, 1e3 * tProduce / timedSteps, 1e3 * tEnqueue / timedSteps,
+         1e3 * tWait / timedSteps, checksum);
   return 0;
 }
