@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
+#include <tuple>
 
 #include "fir_dispatch.h"
 #include "fir_kernels.cuh"
@@ -28,6 +31,15 @@ int envInt(const char* name, int fallback) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : fallback;
 }
+// the routing knobs are read once per process (they exist for experiments, not for switching routes between two calls)
+struct FirEnv {
+  int forceDirect = envInt("B200SDR_FORCE_DIRECT", 0), rpt = envInt("B200SDR_RPT", 0), noWindow = envInt("B200SDR_NO_WINDOW", 0),
+      noWideRows = envInt("B200SDR_NO_WIDE_ROWS", 0);
+};
+const FirEnv& firEnv() {
+  static const FirEnv env;
+  return env;
+}
 
 template <bool STAGED>
 Kernel directKernelForT(int elem, bool tapc, bool mix) {
@@ -48,18 +60,31 @@ Kernel directKernelFor(int elem, bool tapc, bool mix, bool staged) {
 
 }  // namespace
 
+cudaError_t ensureDynamicSmem(const void* kernel, int bytes) {
+  static std::mutex mutex;
+  static std::set<std::tuple<int, const void*, int>> done;
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mutex);
+  if (done.count({device, kernel, bytes})) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.insert({device, kernel, bytes});
+  return e;
+}
+
 FirRoute planFir(int elem, bool tapsComplex, const void* in, unsigned T, unsigned D, int mod) {
   FirRoute r {};
   r.rows = false;
   r.M = D ? (T + D - 1) / D : 0;
-  const bool forceDirect = envInt("B200SDR_FORCE_DIRECT", 0) != 0;
+  const bool forceDirect = firEnv().forceDirect != 0;
   if (forceDirect || tapsComplex || elem == kElemReal || T == 0 || D == 0) return r;
   const unsigned es = elem == kElemInt8Complex ? 2u : 8u;
   const unsigned vec = 16u / es;
   if (D % vec != 0 || (reinterpret_cast<uintptr_t>(in) & 15u) != 0 || r.M > 8) return r;
   r.MP = r.M;
   r.TS = static_cast<unsigned>(tapStride(static_cast<int>(r.MP)));
-  const int forcedRpt = envInt("B200SDR_RPT", 0);
+  const int forcedRpt = firEnv().rpt;
   const unsigned fm = mod == kModFm ? 1u : 0u;
   for (int rptIdx = 1; rptIdx >= 0; rptIdx--) {
     const unsigned rpt = rptIdx ? rowsRptHigh(r.MP) : 1u;
@@ -91,7 +116,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
     prm.outPerTile = route.outPerTile;
     const Kernel k = rowsKernelFor(elem, mix, route.MP, route.rptIdx);
     if (route.smemBytes > 48 * 1024) {
-      const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+      const cudaError_t e = ensureDynamicSmem(reinterpret_cast<const void*>(k), static_cast<int>(kMaxDynSmem));
       if (e != cudaSuccess) return e;
     }
     const unsigned long long blocks = (prm.nOut + route.outPerTile - 1) / route.outPerTile;
@@ -103,7 +128,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
   // row.  Few outputs per input sample, so the cell is HBM-bound and wants the tile streamed ONCE by TMA; the window kernel would
   // walk the D phases in D / 4 strided passes.
   if (elem == kElemComplex && !tapsComplex && !mix && route.M > 8 && route.M <= 32 && prm.D >= 16 && prm.D % 2 == 0 &&
-      (reinterpret_cast<uintptr_t>(prm.in) & 15u) == 0 && envInt("B200SDR_NO_WIDE_ROWS", 0) == 0) {
+      (reinterpret_cast<uintptr_t>(prm.in) & 15u) == 0 && firEnv().noWideRows == 0) {
     const unsigned MP = route.M <= 16 ? 16u : 32u, fm = prm.mod == kModFm ? 1u : 0u;
     const unsigned rpt = (MP == 16 && 2u * kRowsThreads * rowsRowStride(prm.D, 8) <= 64u * 1024u) ? 2u : 1u;
     const unsigned rowsPerTile = rpt * kRowsThreads;
@@ -113,7 +138,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
       prm.outPerTile = rowsPerTile - (route.M - 1) - fm;
       const Kernel k = kRowsCf32PlainWide[MP == 16 ? (rpt == 2 ? 1 : 0) : 2];
       if (lay.total > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+        const cudaError_t e = ensureDynamicSmem(reinterpret_cast<const void*>(k), static_cast<int>(kMaxDynSmem));
         if (e != cudaSuccess) return e;
       }
       const unsigned long long blocks = (prm.nOut + prm.outPerTile - 1) / prm.outPerTile;
@@ -122,7 +147,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
       return launchStatus();
     }
   }
-  if (envInt("B200SDR_NO_WINDOW", 0) == 0 && windowEligible(elem, tapsComplex, mix, prm)) return launchWindow(elem, prm, stream);
+  if (firEnv().noWindow == 0 && windowEligible(elem, tapsComplex, mix, prm)) return launchWindow(elem, prm, stream);
   const unsigned outPerBlock = prm.mod == kModFm ? kDirectThreads - 1 : kDirectThreads;
   const unsigned long long blocks = (prm.nOut + outPerBlock - 1) / outPerBlock;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidConfiguration;
@@ -132,7 +157,7 @@ cudaError_t launchFir(int elem, bool tapsComplex, bool mix, FirParams prm, cudaS
   const unsigned smemBytes = kDirectFixedSmem + (staged ? static_cast<unsigned>(tileBytes) : 0u);
   const Kernel k = directKernelFor(elem, tapsComplex, mix, staged);
   if (smemBytes > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+    const cudaError_t e = ensureDynamicSmem(reinterpret_cast<const void*>(k), static_cast<int>(kMaxDynSmem));
     if (e != cudaSuccess) return e;
   }
   k<<<static_cast<unsigned>(blocks), kDirectThreads, smemBytes, stream>>>(prm);
@@ -153,7 +178,7 @@ cudaError_t launchFirBatched(int elem, FirParams prm, unsigned batch, cudaStream
   const unsigned smemBytes = kDirectFixedSmem + (staged ? static_cast<unsigned>(tileBytes) : 0u);
   const Kernel k = directKernelFor(elem, false, false, staged);
   if (smemBytes > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxDynSmem));
+    const cudaError_t e = ensureDynamicSmem(reinterpret_cast<const void*>(k), static_cast<int>(kMaxDynSmem));
     if (e != cudaSuccess) return e;
   }
   k<<<dim3(static_cast<unsigned>(blocks), batch), kDirectThreads, smemBytes, stream>>>(prm);

@@ -29,6 +29,10 @@ bool windowEligible(int elem, bool tapsComplex, bool mix, const FirParams& prm);
 cudaError_t launchWindow(int elem, FirParams prm, cudaStream_t stream);
 cudaError_t launchWindowBatched(int elem, FirParams prm, unsigned batch, cudaStream_t stream);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size): the FIR entry points are called per block
+// of a stream and the attribute call is a driver round trip
+cudaError_t ensureDynamicSmem(const void* kernel, int bytes);
+
 // rows per thread of the high-RPT variant for MP partial sums (register budget)
 constexpr unsigned rowsRptHigh(unsigned MP) { return MP <= 4 ? 4u : 2u; }
 

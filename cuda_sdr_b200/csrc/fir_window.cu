@@ -263,7 +263,7 @@ cudaError_t launchWindowT(FirParams prm, unsigned batch, cudaStream_t stream) {
                                : pc == 2 ? windowKernel<Elem, 2, kWinR, PAIR>
                                          : windowKernel<Elem, 1, kWinR, PAIR>;
   if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(k), cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const cudaError_t e = ensureDynamicSmem(reinterpret_cast<const void*>(k), 100 * 1024);
     if (e != cudaSuccess) return e;
   }
   if (batch == 0 || batch > 65535u) return cudaErrorInvalidConfiguration;
