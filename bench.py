@@ -575,7 +575,7 @@ def run_chain(args, ctx):
 
     # warm-up, part 1b (N > 1, balanced): the rate of every GPU UNDER THE CONDITIONS OF THE TIMED REGION -- rehearsals of exactly
     # what is timed below (all ranks start together after a barrier, the same number of steps, the gather active, rank 0
-    # absorbing the others' audio), each rank timing its own kernels with one event pair around the whole run.  The GPUs of a box
+    # absorbing the others' audio), each rank timing its own kernels with one event pair around the whole run (median of five).  The GPUs of a box
     # differ by a few per cent and power capping moves them further apart under load; a rate measured on each GPU alone, or over
     # a few kernels, misjudges exactly the ranks that matter.  Two rounds: equal segments first, then a damped correction.
     shares = rates = None
@@ -585,7 +585,7 @@ def run_chain(args, ctx):
         cal_a, cal_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for rnd in range(2):
             times = []
-            for _ in range(2):
+            for _ in range(5):
                 quiesce()
                 cal_a.record()
                 run_steps(args.steps)
@@ -593,7 +593,7 @@ def run_chain(args, ctx):
                 quiesce()
                 times.append(cal_a.elapsed_time(cal_b))
                 extra += args.steps
-            mine = min(times)  # ms for this rank's share of args.steps steps
+            mine = statistics.median(times)  # ms for this rank's share of args.steps steps (a GPU's rate moves between windows)
             all_ms = [t if t > 0 else 1.0 for t in ctx.gather_objects(mine)]
             mean_ms = sum(all_ms) / world
             damp = 1.0 if rnd == 0 else 0.7
