@@ -120,7 +120,11 @@ def test_fir_fc_vs_oracle(ops, T, D, n):
 # the corners and the diagonal of bench.py --workload firsweep (T in 32..4096, D in 1..64), every kernel the
 # dispatcher picks for them (rows, staged direct, window with 5 / 4 / 2 / 1 phases per pass and one or several tap chunks)
 SWEEP_SHAPES = [(4096, 64, 1 << 20), (4096, 1, 30000), (1024, 64, 1 << 20), (32, 64, 1 << 19), (32, 1, 20000), (512, 32, 1 << 19),
-                (256, 16, 1 << 18), (128, 8, 1 << 17), (64, 4, 1 << 16), (2048, 2, 40000), (4096, 16, 1 << 19), (1024, 5, 1 << 17)]
+                (256, 16, 1 << 18), (128, 8, 1 << 17), (64, 4, 1 << 16), (2048, 2, 40000), (4096, 16, 1 << 19), (1024, 5, 1 << 17),
+                # the 16- and 32-partial rows kernels: full (M = 16, 32), padded (M = 19, 15, 9, 25), one and two rows per thread,
+                # rows with and without the 16-byte padding (D * 8 a multiple of 64 or not)
+                (1024, 32, 1 << 19), (512, 16, 1 << 18), (2048, 64, 1 << 20), (1000, 32, 1 << 19), (600, 32, 1 << 18), (300, 20, 1 << 17),
+                (400, 16, 1 << 17), (290, 34, 1 << 17), (1200, 48, 1 << 19)]
 
 
 @pytest.mark.parametrize("T,D,n", SWEEP_SHAPES)
