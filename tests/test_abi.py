@@ -83,3 +83,45 @@ def test_no_cpu_fallback(native):
         ops.int8_to_norm_float(torch.zeros(16, dtype=torch.int8))
     with pytest.raises(native.NativeError):
         Chain(1e6, 1e3, np.ones(8, np.float32), 4)
+
+
+def test_gather_create_rejects_bad_arguments_without_gpu(native):
+    """b200sdr_gather_create validates its configuration before it touches CUDA or NCCL (include/b200sdr/b200sdr.h)."""
+    cfg = native.GatherConfig()
+    handle = ctypes.c_void_p()
+    counts = (ctypes.c_size_t * 2)(16, 16)
+    create = native.lib.b200sdr_gather_create
+    assert create(None, ctypes.byref(handle)) == 4
+    cfg.struct_size = 5
+    assert create(ctypes.byref(cfg), ctypes.byref(handle)) == 4 and b"struct_size" in native.lib.b200sdr_last_error()
+    cfg.struct_size = ctypes.sizeof(native.GatherConfig)
+    cfg.rank, cfg.world, cfg.slabs, cfg.floats_per_rank = 2, 2, 3, counts   # rank out of range
+    assert create(ctypes.byref(cfg), ctypes.byref(handle)) == 4
+    cfg.rank, cfg.slabs = 0, 1                                              # a ring needs two slabs
+    assert create(ctypes.byref(cfg), ctypes.byref(handle)) == 4
+    cfg.slabs, cfg.mode = 3, 3                                              # unknown transport
+    assert create(ctypes.byref(cfg), ctypes.byref(handle)) == 4 and b"mode" in native.lib.b200sdr_last_error()
+    cfg.mode = 0                                                            # NCCL transport without the unique id
+    assert create(ctypes.byref(cfg), ctypes.byref(handle)) == 4 and b"nccl_unique_id" in native.lib.b200sdr_last_error()
+    assert not handle.value
+
+
+def test_config_structs_match_the_header(native, tmp_path):
+    """sizeof / offsetof of the C-ABI's configuration structs as gcc sees the header == the ctypes mirrors in _native.py."""
+    probe = tmp_path / "layout.c"
+    probe.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include <b200sdr/b200sdr.h>\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu %zu %zu %d %d %d\\n", sizeof(b200sdr_gather_config), offsetof(b200sdr_gather_config, floats_per_rank),\n'
+        '         offsetof(b200sdr_gather_config, nccl_unique_id), offsetof(b200sdr_gather_config, mode),\n'
+        '         (int)B200SDR_GATHER_NCCL, (int)B200SDR_GATHER_PEER, (int)B200SDR_GATHER_PEER_COPY);\n'
+        '  printf("%zu\\n", sizeof(b200sdr_chain_config));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    cuda_inc = "/usr/local/cuda/include"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, str(probe), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    G = native.GatherConfig
+    assert [int(v) for v in out[:4]] == [ctypes.sizeof(G), G.floats_per_rank.offset, G.nccl_unique_id.offset, G.mode.offset]
+    from cuda_sdr_b200 import sharding
+    assert [int(v) for v in out[4:7]] == [sharding.Gather.NCCL, sharding.Gather.PEER, sharding.Gather.PEER_COPY]
+    assert int(out[7]) == ctypes.sizeof(native.ChainConfig)
