@@ -9,7 +9,8 @@
 //   --mode component   the same, with the RF-to-audio part built by createFilter("Component", json) in the reference's
 //                      schema (FilterDriverFactory.cpp:27-179) -- the exposed input port is mapped onto Multiply port 1 and
 //                      the cosine onto port 0 (a NON-identity mapping), the output through a PortRemappingSource
-//                      (--input cf32: complex-float samples from the host, no Int8ToFloat node)
+//                      (--input cf32: complex-float samples from the host, no Int8ToFloat node;
+//                       --source file: the FileReader node of the library reads --in itself)
 //   --mode elementwise host cf32 -> H2D -> PassThrough (an out-of-tree filter derived from BaseFilter) ->
 //                      AddConstToVectorLength -> Magnitude -> AddConst -> monitor(D2H) -> host
 // Prints one JSON line; --chunks FILE receives the element count of every cosine readOutput (the reference's float32
@@ -223,7 +224,7 @@ static int memcpyMode(IFactories* f, ICudaCommandQueue* queue) {
 }
 
 struct Args {
-  string mode = "stepping", in, out, taps1, taps2, mod = "am", dot, chunks, input = "int8";
+  string mode = "stepping", in, out, taps1, taps2, mod = "am", dot, chunks, input = "int8", source = "host";
   double fs = 19.2e6, freq = 0, dev = 75e3, addMag = 0.25, addConst = -0.125;
   size_t d1 = 1, d2 = 1, chunk = 262144;
 };
@@ -252,6 +253,7 @@ int main(int argc, char** argv) {
     else if (k == "--dot") a.dot = v;
     else if (k == "--chunks") a.chunks = v;
     else if (k == "--input") a.input = v;
+    else if (k == "--source") a.source = v;
     else if (k == "--fs") a.fs = atof(v.c_str());
     else if (k == "--freq") a.freq = atof(v.c_str());
     else if (k == "--dev") a.dev = atof(v.c_str());
@@ -286,8 +288,15 @@ int main(int argc, char** argv) {
   ConstRef<HostSource> hostSource(new HostSource(input, a.chunk, f->getSysMemCopier()));
   ConstRef<Filter> h2d = unwrap(f->getCudaMemcpyFilterFactory()->createCudaMemcpy(cudaMemcpyHostToDevice, queue));
   Ref<IFilterDriver> inputPipeline = unwrap(f->getFilterDriverFactory()->createFilterDriver());
-  THROW_IF_ERR(inputPipeline->connect(hostSource.get(), 0, h2d, 0));
-  THROW_IF_ERR(inputPipeline->setupNode(hostSource.get(), "Host samples"));
+  // --source file: the samples come from the library's own FileReader node (FileReader.cpp:48-67) instead of the stand-in above
+  Ref<Source> fileSource;
+  Source* sourceNode = hostSource.get();
+  if (a.source == "file") {
+    fileSource = unwrap(f->getFileReaderFactory()->createFileReader(a.in.c_str()));
+    sourceNode = fileSource.get();
+  }
+  THROW_IF_ERR(inputPipeline->connect(sourceNode, 0, h2d, 0));
+  THROW_IF_ERR(inputPipeline->setupNode(sourceNode, a.source == "file" ? "Read samples from a file" : "Host samples"));
   THROW_IF_ERR(inputPipeline->setupNode(h2d, "Copy samples to GPU memory"));
   Ref<Filter> middle;
   size_t outElemBytes = 4;
@@ -407,7 +416,7 @@ int main(int argc, char** argv) {
     const size_t before = monitor->getByteCountRead(0);
     THROW_IF_ERR(driver->doFilter());
     steps++;
-    idle = (monitor->getByteCountRead(0) == before && hostSource->exhausted()) ? idle + 1 : 0;
+    idle = (monitor->getByteCountRead(0) == before && (a.source == "file" || hostSource->exhausted())) ? idle + 1 : 0;
   }
   cudaSetDevice(queue->cudaDevice());
   cudaStreamSynchronize(queue->cudaStream());

@@ -128,6 +128,18 @@ def test_stepping_driver_graph_matches_the_oracle(tmp_path, mod):
         assert name in dot, dot
 
 
+def test_file_reader_node_feeds_the_graph(tmp_path):
+    """The ingest row of SURVEY 8(f2): the library's FileReader node (64 KiB reads, FileReader.cpp:48-67) is the source of the
+    same nested-driver graph; counts exact, audio against the cascade oracle over the chunk sizes the run really used."""
+    exe = build_probe()
+    n = (1 << 20) + 4321
+    x, t1, t2 = chain_inputs(tmp_path, n, seed=57)
+    got, info, log, dot = run_probe(exe, tmp_path, "stepping", "file", chain_args(tmp_path, "am") + ["--source", "file"])
+    check_against(got, info, log, x, t1, t2, "am", "graph fed by the FileReader node vs cascade oracle")
+    assert dot.startswith("digraph") and "Input Pipeline" in dot
+    assert info["steps"] > 8
+
+
 @pytest.mark.parametrize("mod", ["am", "fm"])
 def test_component_json_graph_with_port_remapping(tmp_path, mod):
     """The same chain from createFilter("Component", json) in the reference's schema: nodes keyed by id with inline
