@@ -2,10 +2,14 @@
 // Layout facts are the ones measured on the reference's headers in SURVEY.md section 8(b).
 #include <gpusdrpipeline/Factories.h>
 #include <gpusdrpipeline/FusedChain.h>
+#include <gpusdrpipeline/filters/BaseFilter.h>
 
 #include <cstddef>
 #include <cstdio>
+#include <cstring>
+#include <string>
 #include <type_traits>
+#include <vector>
 
 static_assert(sizeof(Status) == 4 && Status_ParseError == 9, "Status is uint32_t with ten codes in fixed order");
 static_assert(SampleType_FloatComplex == 0 && SampleType_Float == 1 && SampleType_Int8Complex == 2, "SampleType values");
@@ -18,7 +22,60 @@ static_assert(std::is_same<Result<IBuffer>, RefResult<IBuffer>>::value && std::i
 static_assert(std::is_base_of<Sink, Filter>::value && std::is_base_of<Source, Filter>::value && std::is_base_of<Node, IDriver>::value, "hierarchy");
 static_assert(std::is_base_of<IDriver, IFilterDriver>::value && std::is_base_of<Filter, IFilterDriver>::value, "IFilterDriver is a driver and a Filter");
 
-int main() {
+// host end of the host-only graph below: appends whatever the driver hands it to a system-memory buffer
+class CollectSink final : public Sink {
+ public:
+  CollectSink(IBuffer* storage, IBufferSliceFactory* slices) : mStorage(storage), mSlices(slices) {}
+  Result<IBuffer> requestBuffer(size_t, size_t byteCount) noexcept final {
+    if (mStorage->range()->remaining() < byteCount) return ERR_RESULT(Status_OutOfMemory);
+    return mSlices->sliceRemaining(mStorage.get());
+  }
+  Status commitBuffer(size_t, size_t byteCount) noexcept final { return mStorage->range()->increaseEndOffset(byteCount); }
+  size_t preferredInputBufferSize(size_t) noexcept final { return size_t(1) << 16; }
+
+ private:
+  ConstRef<IBuffer> mStorage;
+  ConstRef<IBufferSliceFactory> mSlices;
+  REF_COUNTED(CollectSink);
+};
+
+// an out-of-tree Filter on the published helper base class with SYSTEM-memory port buffers: copies its input through
+class HostPassThrough final : public BaseFilter {
+ public:
+  static Ref<Filter> create(IFactories* f) {
+    ConstRef<IRelocatableResizableBufferFactory> buffers = unwrap(f->createRelocatableSysMemBufferFactory());
+    std::vector<ImmutableRef<IBufferCopier>> copiers;
+    copiers.emplace_back(f->getSysMemCopier());
+    return Ref<Filter>(new HostPassThrough(buffers.get(), f->getBufferSliceFactory(), std::move(copiers), f->getSysMemCopier()));
+  }
+  size_t getOutputDataSize(size_t port) noexcept final {
+    if (port != 0) return 0;
+    Result<IBuffer> in = getPortInputBuffer(0);
+    if (in.status != Status_Success) return 0;
+    ConstRef<IBuffer> hold(in.value);
+    return hold->range()->used();
+  }
+  size_t getOutputSizeAlignment(size_t) noexcept final { return 1; }
+  size_t preferredInputBufferSize(size_t) noexcept final { return size_t(1) << 16; }
+  Status readOutput(IBuffer** bufs, size_t) noexcept final {
+    Ref<IBuffer> in;
+    UNWRAP_OR_FWD_STATUS(in, getPortInputBuffer(0));
+    size_t n = in->range()->used();
+    if (n > bufs[0]->range()->remaining()) n = bufs[0]->range()->remaining();
+    FWD_IF_ERR(mCopier->copy(bufs[0]->writePtr(), in->readPtr(), n));
+    FWD_IF_ERR(bufs[0]->range()->increaseEndOffset(n));
+    return consumeInputBytesAndMoveUsedToStart(0, n);
+  }
+
+ private:
+  HostPassThrough(IRelocatableResizableBufferFactory* buffers, IBufferSliceFactory* slices, std::vector<ImmutableRef<IBufferCopier>>&& copiers,
+                  IBufferCopier* copier)
+      : BaseFilter(buffers, slices, 1, std::move(copiers)), mCopier(copier) {}
+  ConstRef<IBufferCopier> mCopier;
+  REF_COUNTED(HostPassThrough);
+};
+
+int main(int argc, char** argv) {
   gslogSetVerbosity(GSLOG_FATAL);
   Result<IFactories> r = getFactoriesSingleton();
   if (r.status != Status_Success || r.value == nullptr) return 1;
@@ -92,6 +149,42 @@ int main() {
   for (const char* name : {"AacWriter", "AddConst", "AddConstToVectorLength", "Component", "Cosine", "File", "Fir", "HackRfSource", "Int8ToFloat",
                            "Magnitude", "MultiplyCCC", "QuadDemod"})
     if (!hasNodeFactory(name)) return 38;
+
+  // A graph of host-only nodes runs without a GPU: FileReader -> ReadByteCountMonitor(BaseFilter pass-through) -> host sink under ISteppingDriver::connect
+  // + doFilter() (SteppingDriver.cpp:193-366); every byte arrives once and in order, the monitor counts them, DriverToDot names
+  // the nodes.  argv[1] = a scratch file this block writes.
+  if (argc > 1) {
+    std::vector<uint8_t> bytes(200000 + 37);
+    for (size_t i = 0; i < bytes.size(); i++) bytes[i] = static_cast<uint8_t>((i * 2654435761u) >> 13);
+    FILE* out = fopen(argv[1], "wb");
+    if (out == nullptr || fwrite(bytes.data(), 1, bytes.size(), out) != bytes.size()) return 40;
+    fclose(out);
+    ConstRef<Source> reader = unwrap(f->getFileReaderFactory()->createFileReader(argv[1]));
+    Ref<Filter> through = HostPassThrough::create(f);
+    ConstRef<IReadByteCountMonitor> monitor = unwrap(f->getReadByteCountMonitorFactory()->create(through.get()));
+    ConstRef<IBuffer> storage = unwrap(buffers->createBuffer(bytes.size() + (size_t(1) << 17)));
+    ConstRef<CollectSink> sink(new CollectSink(storage, f->getBufferSliceFactory()));
+    Ref<ISteppingDriver> driver = unwrap(f->getSteppingDriverFactory()->createSteppingDriver());
+    if (driver->connect(reader.get(), 0, monitor.get(), 0) != Status_Success || driver->connect(monitor.get(), 0, sink.get(), 0) != Status_Success)
+      return 41;
+    if (driver->setupNode(reader.get(), "Read the file") != Status_Success || driver->setupNode(monitor.get(), "Pass through, counted") != Status_Success ||
+        driver->setupNode(sink.get(), "Collect") != Status_Success)
+      return 42;
+    size_t steps = 0;
+    while (monitor->getByteCountRead(0) < bytes.size() && steps < 1000) {
+      if (driver->doFilter() != Status_Success) return 43;
+      steps++;
+    }
+    if (steps < 3 || monitor->getByteCountRead(0) != bytes.size() || storage->range()->used() != bytes.size()) return 44;  // 64 KiB per pass
+    if (std::memcmp(storage->readPtr(), bytes.data(), bytes.size()) != 0) return 45;
+    if (driver->doFilter() != Status_Success || storage->range()->used() != bytes.size()) return 46;  // end of file: nothing more, no error
+    ConstRef<IDriverToDiagram> toDot = unwrap(f->getDriverToDotFactory()->create());
+    const size_t need = unwrap(toDot->convertToDot(driver.get(), "host_graph", nullptr, 0));
+    std::string text(need, '\0');
+    (void)unwrap(toDot->convertToDot(driver.get(), "host_graph", text.data(), text.size()));
+    if (text.find("digraph") != 0 || text.find("Read the file") == std::string::npos || text.find("->") == std::string::npos) return 47;
+    if (createNode("File", "{\"fileName\": \"/nonexistent/b200sdr\"}").status == Status_Success) return 48;
+  }
 
   // no CPU fallback: with no CUDA device every GPU-facing creation fails with a Status, never with a crash
   int deviceCount = 0;
