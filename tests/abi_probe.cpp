@@ -184,6 +184,22 @@ int main(int argc, char** argv) {
     (void)unwrap(toDot->convertToDot(driver.get(), "host_graph", text.data(), text.size()));
     if (text.find("digraph") != 0 || text.find("Read the file") == std::string::npos || text.find("->") == std::string::npos) return 47;
     if (createNode("File", "{\"fileName\": \"/nonexistent/b200sdr\"}").status == Status_Success) return 48;
+
+    // the same source inside a "Component" (reference schema, FilterDriverFactory.cpp:27-179): a "File" node exposed as output
+    // port 0 through PortRemappingSource; the Component is the Source of the outer stepping driver
+    const std::string json = std::string("{\"nodes\": {\"file\": {\"type\": \"File\", \"fileName\": \"") + argv[1] +
+                             "\"}}, \"connections\": [], \"outputPorts\": [{\"exposedPort\": 0, \"mapped\": {\"node\": \"file\", \"port\": 0}}]}";
+    Result<Node> made = createNode("Component", json.c_str());
+    if (made.status != Status_Success || made.value == nullptr) return 49;
+    ConstRef<Node> component(made.value);
+    if (component->asSource() == nullptr) return 50;
+    ConstRef<IBuffer> storage2 = unwrap(buffers->createBuffer(bytes.size() + (size_t(1) << 17)));
+    ConstRef<CollectSink> sink2(new CollectSink(storage2, f->getBufferSliceFactory()));
+    Ref<ISteppingDriver> outer = unwrap(f->getSteppingDriverFactory()->createSteppingDriver());
+    if (outer->connect(component->asSource(), 0, sink2.get(), 0) != Status_Success) return 51;
+    for (size_t pass = 0; pass < 1000 && storage2->range()->used() < bytes.size(); pass++)
+      if (outer->doFilter() != Status_Success) return 52;
+    if (storage2->range()->used() != bytes.size() || std::memcmp(storage2->readPtr(), bytes.data(), bytes.size()) != 0) return 53;
   }
 
   // no CPU fallback: with no CUDA device every GPU-facing creation fails with a Status, never with a crash
