@@ -100,6 +100,16 @@ GATHER_TRANSPORT = {
 }
 
 
+def gather_slab_schedule(nsteps, longest):
+    """Steps per slab over a run of nsteps steps: `longest` in the steady state, halving towards the end so that one step of audio
+    is what remains to be moved when the last kernel ends."""
+    sizes, left = [], nsteps
+    while left > 0:
+        sizes.append(min(longest, max(1, left // 2)))
+        left -= sizes[-1]
+    return sizes
+
+
 def config_dict(wl, log2_samples, extra=None):
     """`workload` names the chain (identical in both arms); the block one step processes is a separate key, because the CPU arm
     runs a bounded sample of the GPU arm's block (the metric is a rate)."""
@@ -541,11 +551,7 @@ def run_chain(args, ctx):
     set_partition(None)
 
     def slab_schedule(nsteps):
-        sizes, left = [], nsteps
-        while left > 0:
-            sizes.append(min(ge, max(1, left // 2)))
-            left -= sizes[-1]
-        return sizes
+        return gather_slab_schedule(nsteps, ge)
 
     def run_steps(nsteps, events=None, timed=False):
         """nsteps steps of the chain, slab by slab; events: one (start, end) pair per step around the kernel(s)."""

@@ -34,3 +34,18 @@ def test_reference_arm_line_and_isolation():
     assert rec["config"]["workload"] == bench.config_dict(wl, 28)["workload"]
     assert rec["config"]["samples_per_gpu_per_step"] <= 1 << 26 and rec["config"]["bounded_sample_of_samples_per_gpu_per_step"] == 1 << 28
     assert f"2^{rec['config']['samples_per_gpu_per_step'].bit_length() - 1} samples" in rec["cpu_baseline"]["sample"]
+
+
+def test_gather_slab_schedule():
+    """bench.py's slab lengths: they cover the run exactly, never exceed the slab capacity, never grow, and end with one step."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.gather_slab_schedule(20, 5) == [5, 5, 5, 2, 1, 1, 1]
+    for steps in (1, 2, 3, 7, 20, 200, 1000):
+        for longest in (1, 5, 32):
+            sizes = bench.gather_slab_schedule(steps, longest)
+            assert sum(sizes) == steps and max(sizes) <= longest and sizes[-1] == 1
+            assert all(a >= b for a, b in zip(sizes, sizes[1:]))
